@@ -1,0 +1,133 @@
+/*
+ * napafft.h -- C ABI of libnapafft_b200.so: the B200 (sm_100a) replacement for Napa-FFT3's hot
+ * path.  The reference (pkhuong/Napa-FFT3, Common Lisp) has no FFI layer of its own; its operator
+ * boundary is the set of compiled closures of interface.lisp and the keyword front-ends built on
+ * them.  Each entry point below names the reference interface it replaces (file:line); the
+ * sb-alien forms a maintainer would add on the Lisp side are in INTEGRATION.md and lisp/.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; every function returns a napafft_status (0 = ok) and never
+ *     throws; napafft_last_error() gives the thread-local message of the last failure.
+ *   - complex data = interleaved (re, im) doubles, exactly the storage of an SBCL
+ *     (simple-array (complex double-float) (*)); real data = doubles.
+ *   - synchronous like the reference: a host-pointer call returns when dst is complete.
+ *   - host-pointer entry points stage through the library's page-locked ring (or DMA directly if
+ *     the caller's buffer is already page-locked, see napafft_host_register).
+ *   - *_dev entry points take device pointers (as void*) valid on the current CUDA device plus a
+ *     cudaStream_t (as void*, NULL = default stream) and are asynchronous on that stream.
+ *   - there is no CPU fallback: without a usable CUDA device every compute call fails with
+ *     NAPA_E_NO_DEVICE / NAPA_E_CUDA.
+ */
+#ifndef NAPAFFT_H
+#define NAPAFFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAPAFFT_ABI_VERSION 1
+
+typedef enum {
+    NAPA_OK = 0,
+    NAPA_E_NOT_POW2 = 1,      /* (assert (power-of-two-p n)), easy-interface.lisp:55 */
+    NAPA_E_SHORT_BUFFER = 2,  /* (assert (>= (length vec) n)), easy-interface.lisp:56-57 */
+    NAPA_E_NULL = 3,
+    NAPA_E_BAD_ENUM = 4,      /* ecase failures of interface.lisp:12-31 */
+    NAPA_E_CUDA = 5,
+    NAPA_E_NCCL = 6,
+    NAPA_E_UNSUPPORTED = 7,   /* n > 2^32 (interface.lisp:86) or a misaligned device pointer */
+    NAPA_E_NO_DEVICE = 8
+} napafft_status;
+
+/* direction: interface.lisp:3-4  (1 :fwd) / (-1 :inv :bwd) */
+#define NAPA_FWD 1
+#define NAPA_INV (-1)
+/* scaling: interface.lisp:6-7, factors of interface.lisp:41-48 */
+#define NAPA_SCALE_NONE 0 /* nil, 1  */
+#define NAPA_SCALE_INV 1  /* t, :inv : 1/n */
+#define NAPA_SCALE_SQRT 2 /* sqrt, :sqrt : 1/sqrt n forward, (1/n)/(1/sqrt n) inverse */
+/* windowing: interface.lisp:9-10 */
+#define NAPA_WINDOW_NONE 0
+#define NAPA_WINDOW_REAL 1    /* float, real-sample       */
+#define NAPA_WINDOW_COMPLEX 2 /* complex, complex-sample  */
+/* element type of bit-reverse: interface.lisp:103-104 */
+#define NAPA_ELT_COMPLEX 0
+#define NAPA_ELT_REAL 1
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* Binds the calling process to CUDA device `device` (one process per GPU) and builds nothing
+ * eagerly; plans, twiddle tables and staging buffers are created on first use and memoised,
+ * like %ensure-fft / %ensure-twiddles / %ensure-reverse (interface.lisp:81-163). */
+int napafft_init(int device);
+int napafft_shutdown(void);
+int napafft_abi_version(void);
+const char *napafft_last_error(void);
+/* number of kernel launches issued by this library since napafft_init (bench.py gpu_launches) */
+uint64_t napafft_launch_count(void);
+
+/* ---- host-pointer entry points (what the Lisp easy interface binds) ------------------------ */
+/* Replaces the closures of generate-fft / get-fft / get-windowed-fft (interface.lisp:33-74,
+ * 165-217) as driven by fft / ifft (easy-interface.lisp:44-95).
+ *   src, dst : batch transforms of n complex each, transform b at element b*stride (stride >= n;
+ *              the `start` argument of the reference closures is pointer arithmetic on src/dst).
+ *              src == dst is the in-place call; otherwise the ranges must not overlap.
+ *   dir      : NAPA_FWD  = DIF  (natural in; out natural if in_order else bit-reversed)
+ *              NAPA_INV  = DIT  (in natural if in_order else bit-reversed; natural out)
+ *   window   : NULL or n doubles / n complex (window_type); multiplied into the input after the
+ *              scale factor (gen-support.lisp:105-115).  For NAPA_INV the window is indexed by the
+ *              memory position of the bit-reversed input, i.e. by rev(k) when in_order is set
+ *              (inverse.lisp:9-18, easy-interface.lisp:83-95).
+ *   window_per_batch : 0 = one window shared by all transforms, 1 = window b at b*n.          */
+int napafft_c2c(const double *src, double *dst, size_t n, size_t batch, size_t stride, int dir, int scale,
+                int in_order, const void *window, int window_type, int window_per_batch);
+
+/* Replaces %ensure-reverse / get-reverse / bit-reverse (interface.lisp:103-133,
+ * easy-interface.lisp:10-37): dst[b*stride + i] = src[b*stride + rev(i)], i < n. */
+int napafft_bit_reverse(const void *src, void *dst, size_t n, size_t batch, size_t stride, int elt);
+
+/* Replaces rfft (real.lisp:101-135): src = batch x n doubles (item b at b*n), dst = batch x n
+ * complex (full spectrum, natural order).  The final radix-2 twiddles are the reference's
+ * recurrence table (real.lisp:53-64), rebuilt bit-for-bit on the host by the library. n >= 2. */
+int napafft_rfft(const double *src, double *dst, size_t n, size_t batch, int scale);
+/* Replaces rifft (real.lisp:153-185): src = batch x n complex, dst = batch x n doubles.  Unlike the
+ * reference the host copy of src is left intact (the reference documents it as destroyed). */
+int napafft_rifft(const double *src, double *dst, size_t n, size_t batch, int scale);
+/* Replaces %2rfft (real.lisp:33-48): dst = batch x 2n complex, [0,n) = FFT(v1), [n,2n) = FFT(v2) */
+int napafft_2rfft(const double *v1, const double *v2, double *dst, size_t n, size_t batch, int scale);
+
+/* Page-lock / unlock a caller-owned host range so that the entry points above DMA straight from
+ * and to it (SBCL: a static vector or a pinned foreign block).  Optional. */
+int napafft_host_register(void *ptr, size_t bytes);
+int napafft_host_unregister(void *ptr);
+
+/* ---- device-resident entry points (new exports for throughput paths; same semantics) ------- */
+int napafft_c2c_dev(const void *src, void *dst, size_t n, size_t batch, size_t stride, int dir, int scale,
+                    int in_order, const void *window, int window_type, int window_per_batch, void *stream);
+int napafft_bit_reverse_dev(const void *src, void *dst, size_t n, size_t batch, size_t stride, int elt,
+                            void *stream);
+int napafft_rfft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream);
+int napafft_rifft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream);
+int napafft_2rfft_dev(const void *v1, const void *v2, void *dst, size_t n, size_t batch, int scale, void *stream);
+/* a[b*n + i] *= h[b*h_stride + i]  (pointwise spectrum product; h_stride 0 = shared filter) */
+int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, size_t h_stride, void *stream);
+
+/* plain device-memory helpers so that a non-CUDA host (SBCL) can hold device-resident vectors */
+int napafft_dev_alloc(void **out, size_t bytes);
+int napafft_dev_free(void *p);
+int napafft_dev_upload(void *dst_dev, const void *src_host, size_t bytes);
+int napafft_dev_download(void *dst_host, const void *src_dev, size_t bytes);
+int napafft_dev_sync(void);
+
+/* ---- introspection used by the tests ------------------------------------------------------- */
+/* the numeric scale factor of interface.lisp:41-48 */
+double napafft_scale_factor(size_t n, int dir, int scale);
+/* the reference's radix-2 recurrence table (real.lisp:53-64): out = n/2 complex */
+int napafft_radix2_twiddle(size_t n, int dir, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAPAFFT_H */

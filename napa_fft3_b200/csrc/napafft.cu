@@ -1,0 +1,876 @@
+// napafft.cu -- host side of libnapafft_b200.so: C ABI (include/napafft.h), plan/twiddle caches,
+// pass planner, page-locked staging.  Replaces the L3 layer of the reference
+// (interface.lisp:12-217: generate-fft / %ensure-fft / %ensure-twiddles / %ensure-reverse) and the
+// numeric part of L4 (easy-interface.lisp, real.lisp); keyword parsing and window generation stay
+// in the host language (napa_fft3_b200/*.py here, lisp/ for SBCL).
+#include "napafft_kernels.cuh"
+#include "../../include/napafft.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+using napa::cplx;
+using napa::PassParams;
+
+#define NAPA_API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? NAPA_E_NO_DEVICE : NAPA_E_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define OK(call)                   \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != NAPA_OK) return rc_; \
+    } while (0)
+
+static std::atomic<uint64_t> g_launches{0};
+
+static inline bool pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline int ilog2(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++; return l; }
+
+// ------------------------------------------------------------------------------------------
+// per-process device state (one process per GPU)
+// ------------------------------------------------------------------------------------------
+struct BigTw { cplx *lo = nullptr, *hi = nullptr; int shift = 0; };
+struct PairTable { unsigned *dev = nullptr; int count = 0; };
+
+struct State {
+    std::mutex mu;
+    bool inited = false;
+    int device = -1;
+    cplx *stage_tw[14] = {};
+    std::map<int, BigTw> big;                        // by log2 M
+    std::map<std::pair<size_t, int>, cplx *> r2tw;   // (n, dir) -> n/2 entries (reference recurrence)
+    std::map<int, PairTable> pairs;                  // bit-reversal tile pairs by width
+    cplx *scratch = nullptr; size_t scratch_bytes = 0;
+    // staging for host-pointer calls
+    cudaStream_t stream[2] = {};
+    cudaEvent_t done[2] = {};
+    void *pinned[2] = {}; size_t pinned_bytes = 0;
+    void *dbuf[2] = {}; size_t dbuf_bytes = 0;
+    void *dwin = nullptr; size_t dwin_bytes = 0;
+    size_t chunk_bytes = 32u << 20;
+    bool attrs_set = false;
+};
+static State G;
+
+static int ensure_init() {
+    if (G.inited) return NAPA_OK;
+    return napafft_init(-1);
+}
+
+// W_M^e = exp(-2 pi i e / M), evaluated in long double and rounded once
+static inline cplx unit_root(unsigned long long e, unsigned long long M) {
+    // reduce to the first octant for accuracy
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    e %= M;
+    unsigned long long q8 = (e * 8) / M;             // octant (M >= 8 in all uses, or e == 0)
+    long double c, s;
+    if (M < 8) {
+        long double a = PI2 * (long double)e / (long double)M;
+        c = cosl(a); s = sinl(a);
+    } else {
+        unsigned long long oct = M / 8;
+        unsigned long long r = e - q8 * oct;          // 0 <= r < M/8
+        bool odd = q8 & 1;
+        long double a = PI2 * (long double)(odd ? oct - r : r) / (long double)M;  // in [0, pi/4]
+        long double ca = cosl(a), sa = sinl(a);
+        if (odd) std::swap(ca, sa);                   // angle = (q8+1)*pi/4 - a'
+        // now (ca, sa) = cos/sin of the angle within quadrant (q8/2), offset (q8&1 ? pi/2 - a' : a)
+        switch (q8 >> 1) {
+        case 0: c = ca; s = sa; break;
+        case 1: c = -sa; s = ca; break;
+        case 2: c = -ca; s = -sa; break;
+        default: c = sa; s = -ca; break;
+        }
+    }
+    return make_double2((double)c, (double)(-s));
+}
+
+static int ensure_stage_tw(int l) {
+    if (G.stage_tw[l]) return NAPA_OK;
+    size_t L = (size_t)1 << l;
+    std::vector<cplx> h(L);
+    for (size_t m = 0; m < L; m++) h[m] = unit_root(m, L);
+    CU(cudaMalloc(&G.stage_tw[l], L * sizeof(cplx)));
+    CU(cudaMemcpy(G.stage_tw[l], h.data(), L * sizeof(cplx), cudaMemcpyHostToDevice));
+    return NAPA_OK;
+}
+
+static int ensure_big_tw(int lgM, BigTw *out) {
+    auto it = G.big.find(lgM);
+    if (it != G.big.end()) { *out = it->second; return NAPA_OK; }
+    BigTw t;
+    t.shift = (lgM + 1) / 2;
+    unsigned long long M = 1ull << lgM;
+    size_t nlo = (size_t)1 << t.shift, nhi = (size_t)1 << (lgM - t.shift);
+    std::vector<cplx> lo(nlo), hi(nhi);
+    for (size_t i = 0; i < nlo; i++) lo[i] = unit_root(i, M);
+    for (size_t i = 0; i < nhi; i++) hi[i] = unit_root((unsigned long long)i << t.shift, M);
+    CU(cudaMalloc(&t.lo, nlo * sizeof(cplx)));
+    CU(cudaMalloc(&t.hi, nhi * sizeof(cplx)));
+    CU(cudaMemcpy(t.lo, lo.data(), nlo * sizeof(cplx), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.hi, hi.data(), nhi * sizeof(cplx), cudaMemcpyHostToDevice));
+    G.big[lgM] = t;
+    *out = t;
+    return NAPA_OK;
+}
+
+// real.lisp:53-64 %get-radix-2-twiddle, op for op (separately rounded complex product, libm
+// cos/sin of the same argument) so that rfft/rifft track the reference's own rounding drift.
+static void radix2_twiddle_host(size_t n, int dir, cplx *tw) {
+    const double pi = 3.141592653589793;
+    volatile double a = ((-2.0 * pi) * (double)dir) * (1.0 / (double)n);
+    const double mr = cos(a), mi = sin(a);
+    double rr = dir > 0 ? 1.0 : 0.0, ri = dir > 0 ? 0.0 : 1.0;
+    for (size_t k = 0; k < n / 2; k++) {
+        tw[k] = make_double2(rr, ri);
+        volatile double p0 = rr * mr, p1 = ri * mi, p2 = rr * mi, p3 = ri * mr;   // no FMA contraction
+        rr = p0 - p1; ri = p2 + p3;
+    }
+}
+
+static int ensure_r2tw(size_t n, int dir, cplx **out) {
+    auto key = std::make_pair(n, dir);
+    auto it = G.r2tw.find(key);
+    if (it != G.r2tw.end()) { *out = it->second; return NAPA_OK; }
+    std::vector<cplx> h(std::max<size_t>(n / 2, 1));
+    radix2_twiddle_host(n, dir, h.data());
+    cplx *d;
+    CU(cudaMalloc(&d, h.size() * sizeof(cplx)));
+    CU(cudaMemcpy(d, h.data(), h.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    G.r2tw[key] = d;
+    *out = d;
+    return NAPA_OK;
+}
+
+static int ensure_scratch(size_t bytes) {
+    if (G.scratch_bytes >= bytes) return NAPA_OK;
+    if (G.scratch) { CU(cudaDeviceSynchronize()); CU(cudaFree(G.scratch)); G.scratch = nullptr; G.scratch_bytes = 0; }
+    CU(cudaMalloc(&G.scratch, bytes));
+    G.scratch_bytes = bytes;
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel launch table
+// ------------------------------------------------------------------------------------------
+typedef void (*pass_fn)(const PassParams);
+static pass_fn pass_kernel(int l) {
+    switch (l) {
+    case 4: return napa::fft_pass_kernel<4>;
+    case 5: return napa::fft_pass_kernel<5>;
+    case 6: return napa::fft_pass_kernel<6>;
+    case 7: return napa::fft_pass_kernel<7>;
+    case 8: return napa::fft_pass_kernel<8>;
+    case 9: return napa::fft_pass_kernel<9>;
+    case 10: return napa::fft_pass_kernel<10>;
+    case 11: return napa::fft_pass_kernel<11>;
+    case 12: return napa::fft_pass_kernel<12>;
+    case 13: return napa::fft_pass_kernel<13>;
+    }
+    return nullptr;
+}
+
+static int set_kernel_attrs() {
+    if (G.attrs_set) return NAPA_OK;
+    for (int l = 4; l <= 13; l++) {
+        size_t sm = napa::plan_smem_bytes(l);
+        if (sm > 48 * 1024)
+            CU(cudaFuncSetAttribute((const void *)pass_kernel(l), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+    G.attrs_set = true;
+    return NAPA_OK;
+}
+
+static int launch_pass(int l, PassParams &p, long long ntiles, cudaStream_t st) {
+    OK(ensure_stage_tw(l));
+    p.stage_tw = G.stage_tw[l];
+    if (ntiles <= 0) return NAPA_OK;
+    if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
+    pass_fn fn = pass_kernel(l);
+    NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p);
+    g_launches++;
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// planner
+// ------------------------------------------------------------------------------------------
+static std::vector<int> digits_of(int lg) {
+    if (lg <= 13) return { lg };
+    if (lg <= 23) { int l1 = std::min(10, lg / 2); return { l1, lg - l1 }; }
+    int l1 = std::min(10, lg / 3), l2 = std::min(10, (lg - l1) / 2);
+    return { l1, l2, lg - l1 - l2 };
+}
+
+// interface.lisp:41-48
+static double scale_factor(size_t n, int dir, int mode) {
+    double fn = (double)n;
+    if (mode == NAPA_SCALE_NONE) return 1.0;
+    if (mode == NAPA_SCALE_INV) return 1.0 / fn;
+    return dir > 0 ? 1.0 / sqrt(fn) : (1.0 / fn) / (1.0 / sqrt(fn));
+}
+
+struct C2COpts {
+    int dir, in_order;
+    double scale;              // numeric factor applied on the first load
+    const void *window; int wtype; int wpb;
+    bool rifft_pre = false; const cplx *r2tw = nullptr;
+};
+
+// geometry of digit pass s (0-based) of an item with digits d[0..p)
+static void pass_geometry(const std::vector<int> &d, int s, PassParams &p, long long *tiles_per_item) {
+    int lgA = 0, lgB = 0;
+    for (int i = 0; i < s; i++) lgA += d[i];
+    for (int i = s + 1; i < (int)d.size(); i++) lgB += d[i];
+    const int l = d[s];
+    const long long A = 1LL << lgA, L = 1LL << l, B = 1LL << lgB, C = 1LL << napa::plan_log2c(l);
+    if (lgB > 0) {          // column-like
+        p.G = (int)(B / C);
+        p.s_SA = L * B; p.s_SG = C; p.s_i = B; p.s_q = 1;
+        *tiles_per_item = A * (B / C);
+    } else {                // row-like
+        p.G = 1;
+        p.s_SA = C * L; p.s_SG = 0; p.s_i = 1; p.s_q = L;
+        *tiles_per_item = A / C;
+    }
+    p.d_SA = p.s_SA; p.d_SG = p.s_SG; p.d_i = p.s_i; p.d_q = p.s_q;
+    p.tiles_per_item = (int)*tiles_per_item;
+}
+
+static void first_pass_fusions(PassParams &p, const C2COpts &o, size_t n, bool win_rev) {
+    if (o.scale != 1.0) { p.flags |= napa::PF_SCALE; p.scale = o.scale; }
+    if (o.wtype == NAPA_WINDOW_REAL) p.flags |= napa::PF_WIN_REAL;
+    if (o.wtype == NAPA_WINDOW_COMPLEX) p.flags |= napa::PF_WIN_CPLX;
+    if (o.wtype) {
+        p.window = o.window;
+        p.window_batch_stride = o.wpb ? (long long)n : 0;
+        if (win_rev) p.flags |= napa::PF_WIN_REV;
+    }
+    p.lgN = ilog2(n);
+    if (o.rifft_pre) { p.flags |= napa::PF_RIFFT_PRE; p.r2tw = o.r2tw; p.aux_off = (long long)n; }
+}
+
+static int exec_bitrev(const void *src, void *dst, size_t n, size_t batch, size_t sstride, size_t dstride, int elt,
+                       cudaStream_t st);
+
+// The whole c2c family on device pointers.  src/dst strides in complex elements.
+static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t sstride, size_t dstride,
+                    const C2COpts &o, cudaStream_t st) {
+    if (batch == 0) return NAPA_OK;
+    OK(set_kernel_attrs());
+    const int lg = ilog2(n);
+    const bool inv = o.dir < 0;
+    // window index is the bit-reversed position for an in-order inverse (easy-interface.lisp:83-95)
+    const bool win_rev = inv && o.in_order;
+
+    if (lg <= 3) {
+        napa::TinyParams t{};
+        t.src = src; t.dst = dst; t.src_batch_stride = (long long)sstride; t.dst_batch_stride = (long long)dstride;
+        t.batch = (long long)batch; t.lgn = lg; t.flags = 0;
+        if (o.scale != 1.0) { t.flags |= napa::PF_SCALE; t.scale = o.scale; }
+        if (o.wtype == NAPA_WINDOW_REAL) t.flags |= napa::PF_WIN_REAL;
+        if (o.wtype == NAPA_WINDOW_COMPLEX) t.flags |= napa::PF_WIN_CPLX;
+        t.window = o.window; t.window_batch_stride = o.wpb ? (long long)n : 0;
+        if (win_rev) t.flags |= napa::PF_WIN_REV;
+        if (inv) t.flags |= napa::PF_CONJ_IN | napa::PF_CONJ_OUT;
+        if (inv && !o.in_order) t.flags |= napa::PF_IN_REV;
+        if (!inv && !o.in_order) t.flags |= napa::PF_OUT_REV;
+        if (o.rifft_pre) { t.flags |= napa::PF_RIFFT_PRE; t.r2tw = o.r2tw; }
+        NAPA_LAUNCH(napa::fft_tiny_kernel, (unsigned)((batch + 255) / 256), 256, 0, st, t);
+        g_launches++;
+        CU(cudaGetLastError());
+        return NAPA_OK;
+    }
+
+    std::vector<int> d = digits_of(lg);
+    const int p = (int)d.size();
+
+    if (p == 1) {
+        PassParams pp{};
+        pp.src = src; pp.dst = dst; pp.src_batch_stride = (long long)sstride; pp.dst_batch_stride = (long long)dstride;
+        pp.batch = (long long)batch; pp.tiles_per_item = 1; pp.G = 1;
+        pp.s_i = pp.d_i = 1;
+        pp.flags = napa::PF_Q_IS_BATCH;
+        if (inv) pp.flags |= napa::PF_CONJ_IN | napa::PF_CONJ_OUT;
+        if (inv && !o.in_order) pp.flags |= napa::PF_IN_REV;
+        if (!inv && !o.in_order) pp.flags |= napa::PF_OUT_REV;
+        first_pass_fusions(pp, o, n, win_rev);
+        const long long C = 1LL << napa::plan_log2c(lg);
+        OK(launch_pass(lg, pp, ((long long)batch + C - 1) / C, st));
+        CU(cudaGetLastError());
+        return NAPA_OK;
+    }
+
+    // items per chunk: keep a chunk's working set L2-resident across its passes
+    size_t chunk = std::max<size_t>(1, G.chunk_bytes / (n * sizeof(cplx)));
+    chunk = std::min(chunk, batch);
+
+    const bool natural = o.in_order != 0;
+    if (natural && p == 2) {
+        // natural in -> natural out: column pass into L2-resident scratch, row pass stores transposed
+        OK(ensure_scratch(chunk * n * sizeof(cplx)));
+        BigTw bt; OK(ensure_big_tw(lg, &bt));
+        const long long L1 = 1LL << d[0], L2 = 1LL << d[1];
+        for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+            const size_t nb = std::min(chunk, batch - b0);
+            PassParams p1{}; long long tpi;
+            pass_geometry(d, 0, p1, &tpi);
+            p1.src = src + b0 * sstride; p1.dst = G.scratch;
+            p1.src_batch_stride = (long long)sstride; p1.dst_batch_stride = (long long)n; p1.batch = (long long)nb;
+            p1.flags = napa::PF_TW_STORE | (inv ? napa::PF_CONJ_IN : 0);
+            p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << lg) - 1;
+            first_pass_fusions(p1, o, n, win_rev);
+            if (o.wpb) p1.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
+            OK(launch_pass(d[0], p1, tpi * (long long)nb, st));
+            PassParams p2{};
+            pass_geometry(d, 1, p2, &tpi);
+            p2.src = G.scratch; p2.dst = dst + b0 * dstride;
+            p2.src_batch_stride = (long long)n; p2.dst_batch_stride = (long long)dstride; p2.batch = (long long)nb;
+            p2.flags = inv ? napa::PF_CONJ_OUT : 0;
+            // row k1 = ra*C + q, output k2 -> address k1 + L1*k2
+            p2.d_SA = 1LL << napa::plan_log2c(d[1]); p2.d_SG = 0; p2.d_i = L1; p2.d_q = 1;
+            (void)L2;
+            OK(launch_pass(d[1], p2, tpi * (long long)nb, st));
+        }
+        CU(cudaGetLastError());
+        return NAPA_OK;
+    }
+
+    // bit-reversed pipelines (in place on dst after the first pass), any number of digits
+    if (natural && inv) {
+        // reference order: bit-reverse first, then DIT (easy-interface.lisp:83-95)
+        OK(exec_bitrev(src, dst, n, batch, sstride, dstride, NAPA_ELT_COMPLEX, st));
+        src = dst; sstride = dstride;
+    }
+    for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+        const size_t nb = std::min(chunk, batch - b0);
+        for (int step = 0; step < p; step++) {
+            const int s = inv ? p - 1 - step : step;     // DIT runs the digits last to first
+            PassParams pp{}; long long tpi;
+            pass_geometry(d, s, pp, &tpi);
+            const bool first = step == 0, last = step == p - 1;
+            pp.src = first ? src + b0 * sstride : dst + b0 * dstride;
+            pp.dst = dst + b0 * dstride;
+            pp.src_batch_stride = (long long)(first ? sstride : dstride); pp.dst_batch_stride = (long long)dstride;
+            pp.batch = (long long)nb;
+            int lgB = 0;
+            for (int i = s + 1; i < p; i++) lgB += d[i];
+            if (lgB > 0) {
+                BigTw bt; OK(ensure_big_tw(d[s] + lgB, &bt));
+                pp.tw_lo = bt.lo; pp.tw_hi = bt.hi; pp.tw_shift = bt.shift; pp.tw_mask = (1ull << (d[s] + lgB)) - 1;
+                pp.flags |= inv ? napa::PF_TW_LOAD : napa::PF_TW_STORE;
+            }
+            pp.flags |= inv ? napa::PF_IN_REV : napa::PF_OUT_REV;
+            if (inv && first) pp.flags |= napa::PF_CONJ_IN;
+            if (inv && last) pp.flags |= napa::PF_CONJ_OUT;
+            if (first) {
+                C2COpts oo = o;
+                first_pass_fusions(pp, oo, n, false);
+                if (o.wpb && o.wtype) pp.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
+            }
+            OK(launch_pass(d[s], pp, tpi * (long long)nb, st));
+        }
+    }
+    if (natural && !inv) OK(exec_bitrev(dst, dst, n, batch, dstride, dstride, NAPA_ELT_COMPLEX, st));
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// bit reversal
+// ------------------------------------------------------------------------------------------
+static int ensure_pairs(int w, PairTable *out) {
+    auto it = G.pairs.find(w);
+    if (it != G.pairs.end()) { *out = it->second; return NAPA_OK; }
+    const int A = 5, mb = w - 2 * A;
+    std::vector<unsigned> h;
+    for (unsigned m = 0; m < (1u << mb); m++) {
+        unsigned r = 0;
+        for (int i = 0; i < mb; i++) r |= ((m >> i) & 1u) << (mb - 1 - i);
+        if (m <= r) { h.push_back(m); h.push_back(r); }
+    }
+    PairTable t;
+    t.count = (int)(h.size() / 2);
+    CU(cudaMalloc(&t.dev, h.size() * sizeof(unsigned)));
+    CU(cudaMemcpy(t.dev, h.data(), h.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    G.pairs[w] = t;
+    *out = t;
+    return NAPA_OK;
+}
+
+template <typename E>
+static int exec_bitrev_t(const E *src, E *dst, size_t n, size_t batch, size_t sstride, size_t dstride, cudaStream_t st) {
+    const int w = ilog2(n);
+    if (batch == 0) return NAPA_OK;
+    if (w <= 10) {
+        if (batch > 0x7fffffffULL) return fail(NAPA_E_UNSUPPORTED, "batch too large");
+        auto k = napa::bitrev_small_kernel<E>;
+        NAPA_LAUNCH(k, (unsigned)batch, 256, n * sizeof(E), st, src, dst, w, (long long)sstride, (long long)dstride);
+    } else {
+        PairTable pt; OK(ensure_pairs(w, &pt));
+        long long blocks = (long long)pt.count * (long long)batch;
+        if (blocks > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large");
+        auto k = napa::bitrev_tiled_kernel<E, 5>;
+        NAPA_LAUNCH(k, (unsigned)blocks, 256, 0, st, src, dst, w, (long long)sstride, (long long)dstride, pt.count,
+                    (const unsigned *)pt.dev);
+    }
+    g_launches++;
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+static int exec_bitrev(const void *src, void *dst, size_t n, size_t batch, size_t sstride, size_t dstride, int elt,
+                       cudaStream_t st) {
+    if (elt == NAPA_ELT_COMPLEX) return exec_bitrev_t<cplx>((const cplx *)src, (cplx *)dst, n, batch, sstride, dstride, st);
+    return exec_bitrev_t<double>((const double *)src, (double *)dst, n, batch, sstride, dstride, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// real wrappers on device pointers
+// ------------------------------------------------------------------------------------------
+static double real_scale(int mode) { return mode == NAPA_SCALE_NONE ? 1.0 : mode == NAPA_SCALE_INV ? 0.5 : 1.0 / sqrt(2.0); }
+
+static int exec_rfft(const double *src, cplx *dst, size_t n, size_t batch, int scale, cudaStream_t st) {
+    const size_t h = n / 2;
+    C2COpts o{};
+    o.dir = NAPA_FWD; o.in_order = 1; o.scale = real_scale(scale) * scale_factor(h, NAPA_FWD, scale);
+    OK(exec_c2c((const cplx *)src, dst, h, batch, h, n, o, st));
+    cplx *tw; OK(ensure_r2tw(n, +1, &tw));
+    const long long per = (long long)(h / 2) + 1, total = per * (long long)batch;
+    NAPA_LAUNCH(napa::rfft_post_kernel, (unsigned)((total + 255) / 256), 256, 0, st, dst, (long long)n, (long long)batch,
+                (long long)n, (const cplx *)tw);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+static int exec_rifft(const cplx *src, double *dst, size_t n, size_t batch, int scale, cudaStream_t st) {
+    const size_t h = n / 2;
+    cplx *tw; OK(ensure_r2tw(n, -1, &tw));
+    C2COpts o{};
+    o.dir = NAPA_INV; o.in_order = 1; o.scale = real_scale(scale) * scale_factor(h, NAPA_INV, scale);
+    o.rifft_pre = true; o.r2tw = tw;
+    return exec_c2c(src, (cplx *)dst, h, batch, n, h, o, st);
+}
+
+static int exec_2rfft(const double *v1, const double *v2, cplx *dst, size_t n, size_t batch, int scale, cudaStream_t st) {
+    const long long total = (long long)n * (long long)batch;
+    NAPA_LAUNCH(napa::zip2_kernel, (unsigned)((total + 255) / 256), 256, 0, st, v1, v2, dst, (long long)n, (long long)batch,
+                (long long)n, (long long)(2 * n));
+    g_launches++;
+    C2COpts o{};
+    o.dir = NAPA_FWD; o.in_order = 1; o.scale = scale_factor(n, NAPA_FWD, scale);
+    OK(exec_c2c(dst, dst, n, batch, 2 * n, 2 * n, o, st));
+    const long long per = (long long)(n / 2) + 1, tot2 = per * (long long)batch;
+    NAPA_LAUNCH(napa::split2_post_kernel, (unsigned)((tot2 + 255) / 256), 256, 0, st, dst, (long long)(2 * n), (long long)batch,
+                (long long)n);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// argument checks shared by host and device entry points
+// ------------------------------------------------------------------------------------------
+static int check_c2c_args(const void *src, const void *dst, size_t n, size_t batch, size_t stride, int dir, int scale,
+                          const void *window, int wtype) {
+    if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (!pow2(n)) return fail(NAPA_E_NOT_POW2, "transform size %zu is not a power of two", n);
+    if (n > ((size_t)1 << 32)) return fail(NAPA_E_UNSUPPORTED, "transform size %zu exceeds 2^32 (interface.lisp:86)", n);
+    if (batch > 1 && stride < n) return fail(NAPA_E_SHORT_BUFFER, "stride %zu shorter than the transform (%zu)", stride, n);
+    if (dir != NAPA_FWD && dir != NAPA_INV) return fail(NAPA_E_BAD_ENUM, "direction %d is not 1 / -1", dir);
+    if (scale < 0 || scale > 2) return fail(NAPA_E_BAD_ENUM, "scaling %d is not 0 / 1 / 2", scale);
+    if (wtype < 0 || wtype > 2) return fail(NAPA_E_BAD_ENUM, "windowing %d is not 0 / 1 / 2", wtype);
+    if (wtype && !window) return fail(NAPA_E_NULL, "window type %d given with a NULL window", wtype);
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host staging
+// ------------------------------------------------------------------------------------------
+static int ensure_staging(size_t chunk_bytes_needed) {
+    if (!G.stream[0]) {
+        for (int i = 0; i < 2; i++) {
+            CU(cudaStreamCreateWithFlags(&G.stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&G.done[i], cudaEventDisableTiming));
+        }
+    }
+    if (G.dbuf_bytes < chunk_bytes_needed) {
+        CU(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; i++) {
+            if (G.dbuf[i]) CU(cudaFree(G.dbuf[i]));
+            CU(cudaMalloc(&G.dbuf[i], chunk_bytes_needed));
+        }
+        G.dbuf_bytes = chunk_bytes_needed;
+    }
+    return NAPA_OK;
+}
+static int ensure_pinned(size_t bytes) {
+    if (G.pinned_bytes >= bytes) return NAPA_OK;
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; i++) {
+        if (G.pinned[i]) CU(cudaFreeHost(G.pinned[i]));
+        CU(cudaHostAlloc(&G.pinned[i], bytes, cudaHostAllocDefault));
+    }
+    G.pinned_bytes = bytes;
+    return NAPA_OK;
+}
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+static int upload_window(const void *window, int wtype, size_t count, const void **dev) {
+    *dev = nullptr;
+    if (!wtype) return NAPA_OK;
+    size_t bytes = count * (wtype == NAPA_WINDOW_REAL ? 8 : 16);
+    if (G.dwin_bytes < bytes) {
+        CU(cudaDeviceSynchronize());
+        if (G.dwin) CU(cudaFree(G.dwin));
+        CU(cudaMalloc(&G.dwin, bytes));
+        G.dwin_bytes = bytes;
+    }
+    CU(cudaMemcpyAsync(G.dwin, window, bytes, cudaMemcpyHostToDevice, G.stream[0]));
+    CU(cudaStreamSynchronize(G.stream[0]));
+    *dev = G.dwin;
+    return NAPA_OK;
+}
+
+// Generic chunked host pipeline: for every chunk of items, H2D the inputs (item b at
+// src + b*in_pitch) into a dense device region, run `body`, D2H the dense output region.
+// Two chunks are in flight (two streams, two device buffers) so copies overlap compute.
+struct HostJob {
+    const char *src = nullptr, *src2 = nullptr;            // src2: optional second input, same geometry
+    size_t in_item_bytes = 0, in_pitch = 0;
+    char *dst = nullptr; size_t out_item_bytes = 0, out_pitch = 0;
+    bool inplace = false;                                  // output region aliases the input region
+    size_t batch = 0;
+};
+template <typename Body>
+static int run_host_job(const HostJob &j, Body body) {
+    const size_t in_total = j.in_item_bytes * (j.src2 ? 2 : 1);
+    const size_t per_item = j.inplace ? std::max(in_total, j.out_item_bytes) : in_total + j.out_item_bytes;
+    size_t target = (size_t)256 << 20;                                    // device bytes per chunk
+    if (const char *e = getenv("NAPAFFT_STAGE_MB")) target = (size_t)atoll(e) << 20;
+    const size_t items = std::max<size_t>(1, std::min(j.batch, target / std::max<size_t>(per_item, 1)));
+    OK(ensure_staging(items * per_item));
+    const bool src_pinned = is_pinned(j.src) && (!j.src2 || is_pinned(j.src2));
+    const bool dst_pinned = is_pinned(j.dst);
+    if (!src_pinned || !dst_pinned) OK(ensure_pinned(items * std::max(in_total, j.out_item_bytes)));
+    size_t pending_out[2] = { 0, 0 }, pending_b0[2] = { 0, 0 };
+    auto drain = [&](int slot) -> int {
+        if (!pending_out[slot]) return NAPA_OK;
+        CU(cudaEventSynchronize(G.done[slot]));
+        if (!dst_pinned) {
+            const char *ph = (const char *)G.pinned[slot];
+            for (size_t i = 0; i < pending_out[slot]; i++)
+                memcpy(j.dst + (pending_b0[slot] + i) * j.out_pitch, ph + i * j.out_item_bytes, j.out_item_bytes);
+        }
+        pending_out[slot] = 0;
+        return NAPA_OK;
+    };
+    int slot = 0;
+    for (size_t b0 = 0; b0 < j.batch; b0 += items, slot ^= 1) {
+        const size_t nb = std::min(items, j.batch - b0);
+        OK(drain(slot));
+        cudaStream_t st = G.stream[slot];
+        char *dev_in = (char *)G.dbuf[slot];
+        char *dev_out = j.inplace ? dev_in : dev_in + nb * in_total;
+        for (int which = 0; which < (j.src2 ? 2 : 1); which++) {
+            const char *hs = which ? j.src2 : j.src;
+            char *dd = dev_in + (which ? nb * j.in_item_bytes : 0);
+            if (src_pinned) {
+                CU(cudaMemcpy2DAsync(dd, j.in_item_bytes, hs + b0 * j.in_pitch, j.in_pitch, j.in_item_bytes, nb,
+                                     cudaMemcpyHostToDevice, st));
+            } else {
+                char *ph = (char *)G.pinned[slot] + (which ? nb * j.in_item_bytes : 0);
+                for (size_t i = 0; i < nb; i++) memcpy(ph + i * j.in_item_bytes, hs + (b0 + i) * j.in_pitch, j.in_item_bytes);
+                CU(cudaMemcpyAsync(dd, ph, nb * j.in_item_bytes, cudaMemcpyHostToDevice, st));
+            }
+        }
+        OK(body(dev_in, dev_out, nb, b0, st));
+        if (dst_pinned) {
+            CU(cudaMemcpy2DAsync(j.dst + b0 * j.out_pitch, j.out_pitch, dev_out, j.out_item_bytes, j.out_item_bytes, nb,
+                                 cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(cudaMemcpyAsync(G.pinned[slot], dev_out, nb * j.out_item_bytes, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaEventRecord(G.done[slot], st));
+        pending_out[slot] = nb; pending_b0[slot] = b0;
+    }
+    OK(drain(0));
+    OK(drain(1));
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+NAPA_API int napafft_abi_version(void) { return NAPAFFT_ABI_VERSION; }
+NAPA_API const char *napafft_last_error(void) { return g_err; }
+NAPA_API uint64_t napafft_launch_count(void) { return g_launches.load(); }
+
+NAPA_API int napafft_init(int device) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(NAPA_E_NO_DEVICE, "no CUDA device available (%s); napa-fft3-b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) { if (G.inited) return NAPA_OK; CU(cudaGetDevice(&device)); }
+    if (device >= count) return fail(NAPA_E_NO_DEVICE, "device %d requested but only %d present", device, count);
+    if (G.inited && G.device != device) return fail(NAPA_E_UNSUPPORTED, "already bound to device %d (one process per GPU)", G.device);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(NAPA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
+    G.device = device;
+    G.inited = true;
+    return NAPA_OK;
+}
+
+NAPA_API int napafft_shutdown(void) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited) return NAPA_OK;
+    cudaDeviceSynchronize();
+    for (int l = 0; l < 14; l++) if (G.stage_tw[l]) { cudaFree(G.stage_tw[l]); G.stage_tw[l] = nullptr; }
+    for (auto &kv : G.big) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+    G.big.clear();
+    for (auto &kv : G.r2tw) cudaFree(kv.second);
+    G.r2tw.clear();
+    for (auto &kv : G.pairs) cudaFree(kv.second.dev);
+    G.pairs.clear();
+    if (G.scratch) cudaFree(G.scratch);
+    G.scratch = nullptr; G.scratch_bytes = 0;
+    for (int i = 0; i < 2; i++) {
+        if (G.dbuf[i]) cudaFree(G.dbuf[i]);
+        if (G.pinned[i]) cudaFreeHost(G.pinned[i]);
+        if (G.stream[i]) cudaStreamDestroy(G.stream[i]);
+        if (G.done[i]) cudaEventDestroy(G.done[i]);
+        G.dbuf[i] = G.pinned[i] = nullptr; G.stream[i] = nullptr; G.done[i] = nullptr;
+    }
+    if (G.dwin) cudaFree(G.dwin);
+    G.dwin = nullptr; G.dwin_bytes = G.dbuf_bytes = G.pinned_bytes = 0;
+    G.inited = false;
+    return NAPA_OK;
+}
+
+NAPA_API double napafft_scale_factor(size_t n, int dir, int scale) { return scale_factor(n, dir, scale); }
+
+NAPA_API int napafft_radix2_twiddle(size_t n, int dir, double *out) {
+    if (!out) return fail(NAPA_E_NULL, "out must not be NULL");
+    if (!pow2(n)) return fail(NAPA_E_NOT_POW2, "size %zu is not a power of two", n);
+    radix2_twiddle_host(n, dir, (cplx *)out);
+    return NAPA_OK;
+}
+
+// ---- device-resident entry points ----
+NAPA_API int napafft_c2c_dev(const void *src, void *dst, size_t n, size_t batch, size_t stride, int dir, int scale,
+                             int in_order, const void *window, int window_type, int window_per_batch, void *stream) {
+    OK(check_c2c_args(src, dst, n, batch, stride, dir, scale, window, window_type));
+    if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(NAPA_E_UNSUPPORTED, "device pointers must be 16-byte aligned");
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    C2COpts o{};
+    o.dir = dir; o.in_order = in_order; o.scale = scale_factor(n, dir, scale);
+    o.window = window; o.wtype = window_type; o.wpb = window_per_batch;
+    return exec_c2c((const cplx *)src, (cplx *)dst, n, batch, stride, stride, o, (cudaStream_t)stream);
+}
+
+NAPA_API int napafft_bit_reverse_dev(const void *src, void *dst, size_t n, size_t batch, size_t stride, int elt, void *stream) {
+    if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (!pow2(n)) return fail(NAPA_E_NOT_POW2, "size %zu is not a power of two", n);
+    if (elt != NAPA_ELT_COMPLEX && elt != NAPA_ELT_REAL) return fail(NAPA_E_BAD_ENUM, "element type %d", elt);
+    if (batch > 1 && stride < n) return fail(NAPA_E_SHORT_BUFFER, "stride %zu shorter than n %zu", stride, n);
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    return exec_bitrev(src, dst, n, batch, stride, stride, elt, (cudaStream_t)stream);
+}
+
+static int check_real_args(const void *a, const void *b, size_t n, int scale) {
+    if (!a || !b) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (!pow2(n)) return fail(NAPA_E_NOT_POW2, "size %zu is not a power of two", n);
+    if (n < 2) return fail(NAPA_E_UNSUPPORTED, "real transforms need n >= 2 (real.lisp:10-15 asserts on a size-0 half transform)");
+    if (scale < 0 || scale > 2) return fail(NAPA_E_BAD_ENUM, "scaling %d is not 0 / 1 / 2", scale);
+    return NAPA_OK;
+}
+
+NAPA_API int napafft_rfft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream) {
+    OK(check_real_args(src, dst, n, scale));
+    if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(NAPA_E_UNSUPPORTED, "device pointers must be 16-byte aligned");
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    return exec_rfft((const double *)src, (cplx *)dst, n, batch, scale, (cudaStream_t)stream);
+}
+NAPA_API int napafft_rifft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream) {
+    OK(check_real_args(src, dst, n, scale));
+    if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(NAPA_E_UNSUPPORTED, "device pointers must be 16-byte aligned");
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    return exec_rifft((const cplx *)src, (double *)dst, n, batch, scale, (cudaStream_t)stream);
+}
+NAPA_API int napafft_2rfft_dev(const void *v1, const void *v2, void *dst, size_t n, size_t batch, int scale, void *stream) {
+    OK(check_real_args(v1, dst, n, scale));
+    if (!v2) return fail(NAPA_E_NULL, "v2 must not be NULL");
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    return exec_2rfft((const double *)v1, (const double *)v2, (cplx *)dst, n, batch, scale, (cudaStream_t)stream);
+}
+NAPA_API int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, size_t h_stride, void *stream) {
+    if (!a || !h) return fail(NAPA_E_NULL, "a/h must not be NULL");
+    OK(ensure_init());
+    const long long total = (long long)n * (long long)batch;
+    if (total == 0) return NAPA_OK;
+    NAPA_LAUNCH(napa::cmul_pointwise_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, (cplx *)a,
+                (const cplx *)h, (long long)n, (long long)batch, (long long)h_stride);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+NAPA_API int napafft_dev_alloc(void **out, size_t bytes) {
+    if (!out) return fail(NAPA_E_NULL, "out must not be NULL");
+    OK(ensure_init());
+    CU(cudaMalloc(out, bytes ? bytes : 16));
+    return NAPA_OK;
+}
+NAPA_API int napafft_dev_free(void *p) { if (p) CU(cudaFree(p)); return NAPA_OK; }
+NAPA_API int napafft_dev_upload(void *d, const void *h, size_t bytes) {
+    if (!d || !h) return fail(NAPA_E_NULL, "NULL pointer");
+    CU(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+    return NAPA_OK;
+}
+NAPA_API int napafft_dev_download(void *h, const void *d, size_t bytes) {
+    if (!d || !h) return fail(NAPA_E_NULL, "NULL pointer");
+    CU(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+    return NAPA_OK;
+}
+NAPA_API int napafft_dev_sync(void) { CU(cudaDeviceSynchronize()); return NAPA_OK; }
+
+NAPA_API int napafft_host_register(void *ptr, size_t bytes) {
+    if (!ptr) return fail(NAPA_E_NULL, "NULL pointer");
+    OK(ensure_init());
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return NAPA_OK;
+}
+NAPA_API int napafft_host_unregister(void *ptr) {
+    if (!ptr) return fail(NAPA_E_NULL, "NULL pointer");
+    CU(cudaHostUnregister(ptr));
+    return NAPA_OK;
+}
+
+// ---- host-pointer entry points ----
+NAPA_API int napafft_c2c(const double *src, double *dst, size_t n, size_t batch, size_t stride, int dir, int scale,
+                         int in_order, const void *window, int window_type, int window_per_batch) {
+    OK(check_c2c_args(src, dst, n, batch, stride, dir, scale, window, window_type));
+    if (batch == 0) return NAPA_OK;
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (batch == 1) stride = n;
+    OK(ensure_staging(16));
+    const void *dwin;
+    OK(upload_window(window, window_type, window_per_batch ? n * batch : n, &dwin));
+    HostJob j;
+    j.src = (const char *)src; j.in_item_bytes = n * 16; j.in_pitch = stride * 16;
+    j.dst = (char *)dst; j.out_item_bytes = n * 16; j.out_pitch = stride * 16;
+    j.inplace = true; j.batch = batch;
+    const double sf = scale_factor(n, dir, scale);
+    return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t b0, cudaStream_t st) -> int {
+        C2COpts o{};
+        o.dir = dir; o.in_order = in_order; o.scale = sf;
+        o.wtype = window_type; o.wpb = window_per_batch;
+        o.window = window_per_batch && dwin ? (const char *)dwin + b0 * n * (window_type == NAPA_WINDOW_REAL ? 8 : 16) : dwin;
+        return exec_c2c((const cplx *)din, (cplx *)dout, n, nb, n, n, o, st);
+    });
+}
+
+NAPA_API int napafft_bit_reverse(const void *src, void *dst, size_t n, size_t batch, size_t stride, int elt) {
+    if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (!pow2(n)) return fail(NAPA_E_NOT_POW2, "size %zu is not a power of two", n);
+    if (elt != NAPA_ELT_COMPLEX && elt != NAPA_ELT_REAL) return fail(NAPA_E_BAD_ENUM, "element type %d", elt);
+    if (batch > 1 && stride < n) return fail(NAPA_E_SHORT_BUFFER, "stride %zu shorter than n %zu", stride, n);
+    if (batch == 0) return NAPA_OK;
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (batch == 1) stride = n;
+    const size_t es = elt == NAPA_ELT_COMPLEX ? 16 : 8;
+    HostJob j;
+    j.src = (const char *)src; j.in_item_bytes = n * es; j.in_pitch = stride * es;
+    j.dst = (char *)dst; j.out_item_bytes = n * es; j.out_pitch = stride * es;
+    j.inplace = true; j.batch = batch;
+    return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
+        return exec_bitrev(din, dout, n, nb, n, n, elt, st);
+    });
+}
+
+NAPA_API int napafft_rfft(const double *src, double *dst, size_t n, size_t batch, int scale) {
+    OK(check_real_args(src, dst, n, scale));
+    if (batch == 0) return NAPA_OK;
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    HostJob j;
+    j.src = (const char *)src; j.in_item_bytes = n * 8; j.in_pitch = n * 8;
+    j.dst = (char *)dst; j.out_item_bytes = n * 16; j.out_pitch = n * 16;
+    j.batch = batch;
+    return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
+        return exec_rfft((const double *)din, (cplx *)dout, n, nb, scale, st);
+    });
+}
+
+NAPA_API int napafft_rifft(const double *src, double *dst, size_t n, size_t batch, int scale) {
+    OK(check_real_args(src, dst, n, scale));
+    if (batch == 0) return NAPA_OK;
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    HostJob j;
+    j.src = (const char *)src; j.in_item_bytes = n * 16; j.in_pitch = n * 16;
+    j.dst = (char *)dst; j.out_item_bytes = n * 8; j.out_pitch = n * 8;
+    j.batch = batch;
+    return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
+        return exec_rifft((const cplx *)din, (double *)dout, n, nb, scale, st);
+    });
+}
+
+NAPA_API int napafft_2rfft(const double *v1, const double *v2, double *dst, size_t n, size_t batch, int scale) {
+    OK(check_real_args(v1, dst, n, scale));
+    if (!v2) return fail(NAPA_E_NULL, "v2 must not be NULL");
+    if (batch == 0) return NAPA_OK;
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    HostJob j;
+    j.src = (const char *)v1; j.src2 = (const char *)v2; j.in_item_bytes = n * 8; j.in_pitch = n * 8;
+    j.dst = (char *)dst; j.out_item_bytes = 2 * n * 16; j.out_pitch = 2 * n * 16;
+    j.batch = batch;
+    return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
+        return exec_2rfft((const double *)din, (const double *)(din + nb * n * 8), (cplx *)dout, n, nb, scale, st);
+    });
+}

@@ -1,0 +1,512 @@
+// napafft_kernels.cuh -- sm_100a device code for the Napa-FFT3 hot path (complex-double
+// power-of-two DFTs, bit reversal, fused scale/window, real wrappers).
+//
+// Design: a transform of size N = L_1 * ... * L_p is run as p "digit passes".
+// One CTA owns a TILE of C interleaved length-L sub-transforms (C*L = 4096 or 8192 points):
+//   * column-like tile: C adjacent columns of an [A][L][B] view (element (a,i,b) at a*L*B+i*B+b),
+//     every global access is a C*16-byte contiguous segment;
+//   * row-like tile: C contiguous rows of L points.
+// Each thread keeps 16 points in registers; a pass is a Stockham autosort FFT whose first radix
+// stage is fed straight from global memory and whose last radix stage stores straight to global
+// memory, with shared memory used only for the exchanges in between.  Scale, window, the
+// inter-pass twiddle, conjugation (inverse transforms) and the bit-reversal of the reference's
+// :in-order nil layout are fused into those global loads and stores.
+//
+// Reference semantics being reproduced (file:line into pkhuong/Napa-FFT3):
+//   forward.lisp:54-117 (DIF: natural in, bit-reversed out, scale THEN window on the first load),
+//   inverse.lisp:47-112 (DIT: bit-reversed in, natural out, window indexed by memory position),
+//   gen-support.lisp:44-60 (%scale, %window), bit-reversal.lisp:146-252, real.lisp:10-31,101-185.
+#pragma once
+#ifdef NAPA_EMULATE
+#include "cuda_emul.h"   // tests/emul: CPU functional emulation for the no-GPU test tier only
+#else
+#include <cuda_runtime.h>
+#define NAPA_DYN_SMEM(T, name)                                      \
+    extern __shared__ __align__(16) unsigned char name##_raw[];    \
+    T *name = reinterpret_cast<T *>(name##_raw)
+#define NAPA_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+#include <stdint.h>
+
+namespace napa {
+
+typedef double2 cplx;
+
+// ------------------------------------------------------------------------------------------
+// complex helpers (nvcc contracts a*b+c into DFMA: 2 DMUL + 2 DFMA per complex product)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ cplx mul_mi(cplx a) { return make_double2(a.y, -a.x); }   // * (-i)
+__device__ __forceinline__ cplx mul_pi(cplx a) { return make_double2(-a.y, a.x); }   // * (+i)
+
+#define NAPA_SQRT1_2 0.70710678118654752440
+#define NAPA_COS_PI_8 0.92387953251128675613
+#define NAPA_SIN_PI_8 0.38268343236508977173
+
+// forward (e^{-2 pi i jk/R}) butterflies, natural in -> natural out, in registers
+__device__ __forceinline__ void fft2(cplx &a0, cplx &a1) {
+    cplx t = a0; a0 = cadd(t, a1); a1 = csub(t, a1);
+}
+__device__ __forceinline__ void fft4(cplx &a0, cplx &a1, cplx &a2, cplx &a3) {
+    cplx s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = mul_mi(csub(a1, a3));
+    a0 = cadd(s02, s13); a2 = csub(s02, s13); a1 = cadd(d02, d13); a3 = csub(d02, d13);
+}
+// W_8^1 * z and W_8^3 * z
+__device__ __forceinline__ cplx mul_w8_1(cplx z) { return make_double2((z.x + z.y) * NAPA_SQRT1_2, (z.y - z.x) * NAPA_SQRT1_2); }
+__device__ __forceinline__ cplx mul_w8_3(cplx z) { return make_double2((z.y - z.x) * NAPA_SQRT1_2, -(z.x + z.y) * NAPA_SQRT1_2); }
+
+template <int R> struct Radix;
+template <> struct Radix<2> {
+    static __device__ __forceinline__ void run(cplx *w) { fft2(w[0], w[1]); }
+};
+template <> struct Radix<4> {
+    static __device__ __forceinline__ void run(cplx *w) { fft4(w[0], w[1], w[2], w[3]); }
+};
+template <> struct Radix<8> {
+    // j = a + 2d, k = b + 4c:  W_8^{jk} = W_8^{ab} W_2^{ac} W_4^{db}
+    static __device__ __forceinline__ void run(cplx *w) {
+        fft4(w[0], w[2], w[4], w[6]);          // a = 0: u0[b] in w[0],w[2],w[4],w[6]
+        fft4(w[1], w[3], w[5], w[7]);          // a = 1: u1[b] in w[1],w[3],w[5],w[7]
+        cplx u1 = mul_w8_1(w[3]), u2 = mul_mi(w[5]), u3 = mul_w8_3(w[7]);
+        cplx o0 = cadd(w[0], w[1]), o4 = csub(w[0], w[1]);
+        cplx o1 = cadd(w[2], u1), o5 = csub(w[2], u1);
+        cplx o2 = cadd(w[4], u2), o6 = csub(w[4], u2);
+        cplx o3 = cadd(w[6], u3), o7 = csub(w[6], u3);
+        w[0] = o0; w[1] = o1; w[2] = o2; w[3] = o3; w[4] = o4; w[5] = o5; w[6] = o6; w[7] = o7;
+    }
+};
+template <> struct Radix<16> {
+    // j = a + 4d, k = b + 4c:  W_16^{jk} = W_16^{ab} W_4^{ac} W_4^{db}
+    static __device__ __forceinline__ void run(cplx *w) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) fft4(w[a], w[a + 4], w[a + 8], w[a + 12]);   // w[a+4b] = u[a][b]
+        const cplx W1 = make_double2(NAPA_COS_PI_8, -NAPA_SIN_PI_8);
+        const cplx W3 = make_double2(NAPA_SIN_PI_8, -NAPA_COS_PI_8);
+        w[1 + 4] = cmul(w[1 + 4], W1);            // a=1,b=1: W^1
+        w[1 + 8] = mul_w8_1(w[1 + 8]);            // a=1,b=2: W^2
+        w[1 + 12] = cmul(w[1 + 12], W3);          // a=1,b=3: W^3
+        w[2 + 4] = mul_w8_1(w[2 + 4]);            // a=2,b=1: W^2
+        w[2 + 8] = mul_mi(w[2 + 8]);              // a=2,b=2: W^4 = -i
+        w[2 + 12] = mul_w8_3(w[2 + 12]);          // a=2,b=3: W^6
+        w[3 + 4] = cmul(w[3 + 4], W3);            // a=3,b=1: W^3
+        w[3 + 8] = mul_w8_3(w[3 + 8]);            // a=3,b=2: W^6
+        {                                          // a=3,b=3: W^9 = -W^1
+            cplx t = cmul(w[3 + 12], W1); w[3 + 12] = make_double2(-t.x, -t.y);
+        }
+        cplx o[16];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            cplx x0 = w[4 * b], x1 = w[4 * b + 1], x2 = w[4 * b + 2], x3 = w[4 * b + 3];
+            fft4(x0, x1, x2, x3);                  // output c -> X[b + 4c]
+            o[b] = x0; o[b + 4] = x1; o[b + 8] = x2; o[b + 12] = x3;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = o[i];
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// radix plans: every thread owns 16 points, so a radix-R stage is 16/R butterflies per thread
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int plan_nstages(int l) { return l <= 4 ? 1 : l <= 8 ? 2 : l <= 12 ? 3 : 4; }
+__host__ __device__ constexpr int plan_log2radix(int l, int s) {
+    // l: 4 [16] 5 [8,4] 6 [8,8] 7 [16,8] 8 [16,16] 9 [8,8,8] 10 [16,16,4] 11 [16,16,8]
+    //    12 [16,16,16] 13 [16,16,8,4]
+    switch (l) {
+    case 4: return 4;
+    case 5: return s == 0 ? 3 : 2;
+    case 6: return 3;
+    case 7: return s == 0 ? 4 : 3;
+    case 8: return 4;
+    case 9: return 3;
+    case 10: return s < 2 ? 4 : 2;
+    case 11: return s < 2 ? 4 : 3;
+    case 12: return 4;
+    case 13: return s < 2 ? 4 : (s == 2 ? 3 : 2);
+    }
+    return 0;
+}
+// tile shape: C*L = 4096 points per CTA (8192 for L = 8192); 16 points per thread
+__host__ __device__ constexpr int plan_log2c(int l) { return l <= 12 ? 12 - l : 0; }
+__host__ __device__ constexpr int plan_threads(int l) { return (1 << (l - 4)) << plan_log2c(l); }
+// shared-memory index padding (only needed when C < 8; see tools/bank_check.py)
+__host__ __device__ constexpr int plan_padshift(int l) { return plan_log2c(l) >= 3 ? 31 : 4; }
+__host__ __device__ constexpr size_t plan_smem_bytes(int l) {
+    return plan_nstages(l) == 1 ? 0
+           : (size_t)(((1u << l) + ((1u << l) >> plan_padshift(l))) << plan_log2c(l)) * sizeof(cplx);
+}
+
+enum : unsigned {
+    PF_Q_IS_BATCH = 1u << 0,   // q indexes batch items (single-pass row tiles) instead of rows/cols
+    PF_IN_REV     = 1u << 1,   // logical input i lives at position rev_L(i) along the tile's i axis
+    PF_OUT_REV    = 1u << 2,   // logical output k is stored at position rev_L(k)
+    PF_CONJ_IN    = 1u << 3,
+    PF_CONJ_OUT   = 1u << 4,
+    PF_TW_LOAD    = 1u << 5,   // multiply loads by W_M^{i*col}   (DIT-order pipelines)
+    PF_TW_STORE   = 1u << 6,   // multiply stores by W_M^{k*col}  (DIF-order pipelines)
+    PF_WIN_REAL   = 1u << 7,
+    PF_WIN_CPLX   = 1u << 8,
+    PF_WIN_REV    = 1u << 9,   // window index = rev_{lgN}(offset in transform) (ifft :in-order t)
+    PF_SCALE      = 1u << 10,
+    PF_RIFFT_PRE  = 1u << 11,  // x = (a+b) + (a-b)*r2tw[off], b = src[off + N]   (real.lisp:170-177)
+};
+
+struct PassParams {
+    const cplx *src;
+    cplx *dst;
+    long long src_batch_stride, dst_batch_stride;   // complex elements between batch items
+    long long batch;                                // number of batch items in this launch
+    int tiles_per_item;                             // tiles inside one item (1 if PF_Q_IS_BATCH)
+    int G;                                          // tile r -> (r / G, r % G)
+    long long s_SA, s_SG, s_i, s_q;                 // src offset = (r/G)*SA + (r%G)*SG + pos(i)*s_i + q*s_q
+    long long d_SA, d_SG, d_i, d_q;
+    unsigned flags;
+    double scale;
+    const void *window;                             // double[] or cplx[]
+    long long window_batch_stride;                  // 0 = shared window
+    int lgN;                                        // log2 of the full transform (PF_WIN_REV)
+    const cplx *stage_tw;                           // W_L^m, m < L
+    const cplx *tw_lo, *tw_hi;                      // W_M^e = hi[e >> tw_shift] * lo[e & mask]
+    int tw_shift;
+    unsigned long long tw_mask;                     // M - 1
+    const cplx *r2tw;                               // reference recurrence table (rifft pre-pass)
+    long long aux_off;                              // N for PF_RIFFT_PRE
+};
+
+__device__ __forceinline__ cplx ldg_c(const cplx *p) { return __ldg(p); }
+// rev_w(x): reverse the low w bits of x (w = 0 -> 0)
+__device__ __forceinline__ int rev_bits(int x, int w) { return w ? (int)(__brev((unsigned)x) >> (32 - w)) : 0; }
+__device__ __forceinline__ long long rev_bits64(long long x, int w) {
+    return w ? (long long)(__brevll((unsigned long long)x) >> (64 - w)) : 0;
+}
+
+template <int LOG2L, int STAGE, int LOG2NS>
+struct Stages {
+    static constexpr int L = 1 << LOG2L;
+    static constexpr int T = L / 16;
+    static constexpr int LOG2C = plan_log2c(LOG2L);
+    static constexpr int PADSH = plan_padshift(LOG2L);
+    static constexpr int NSTAGES = plan_nstages(LOG2L);
+    static constexpr int LOG2R = plan_log2radix(LOG2L, STAGE);
+    static constexpr int R = 1 << LOG2R;
+    static constexpr int NB = 16 / R;
+    static constexpr int NS = 1 << LOG2NS;
+
+    static __device__ __forceinline__ int phys(int pos, int q) { return ((pos + (pos >> PADSH)) << LOG2C) + q; }
+
+    static __device__ __forceinline__ void run(cplx (&v)[16], cplx *sm, const cplx *__restrict__ tw, int t, int q) {
+        if constexpr (STAGE > 0) {
+            // exchange: previous stage wrote its scattered outputs; gather t + m*T
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = sm[phys(t + m * T, q)];
+            // twiddle W_{NS*R}^{(jb % NS) * s} on input s of butterfly jb = t + u*T
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                int jm = (t + u * T) & (NS - 1);
+#pragma unroll
+                for (int s = 1; s < R; s++) {
+                    cplx w = ldg_c(tw + (jm * s) * (L / (NS * R)));
+                    v[u + s * NB] = cmul(v[u + s * NB], w);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            cplx w[R];
+#pragma unroll
+            for (int s = 0; s < R; s++) w[s] = v[u + s * NB];
+            Radix<R>::run(w);
+#pragma unroll
+            for (int s = 0; s < R; s++) v[u + s * NB] = w[s];
+        }
+        if constexpr (STAGE + 1 < NSTAGES) {
+            if constexpr (STAGE > 0) __syncthreads();   // everyone has gathered before we overwrite
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                int jb = t + u * T;
+                int base = ((jb >> LOG2NS) << (LOG2NS + LOG2R)) + (jb & (NS - 1));
+#pragma unroll
+                for (int s = 0; s < R; s++) sm[phys(base + s * NS, q)] = v[u + s * NB];
+            }
+            __syncthreads();
+            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R>::run(v, sm, tw, t, q);
+        }
+    }
+};
+
+// W_M^e from the two-level table
+__device__ __forceinline__ cplx big_twiddle(const PassParams &p, unsigned long long e) {
+    e &= p.tw_mask;
+    cplx lo = ldg_c(p.tw_lo + (e & ((1ull << p.tw_shift) - 1)));
+    cplx hi = ldg_c(p.tw_hi + (e >> p.tw_shift));
+    return cmul(hi, lo);
+}
+
+template <int LOG2L>
+__global__ void __launch_bounds__(plan_threads(LOG2L), (plan_threads(LOG2L) <= 256 ? 2 : 1))
+fft_pass_kernel(const PassParams p) {
+    constexpr int L = 1 << LOG2L;
+    constexpr int T = L / 16;
+    constexpr int LOG2C = plan_log2c(LOG2L);
+    constexpr int C = 1 << LOG2C;
+    NAPA_DYN_SMEM(cplx, sm);
+
+    const int tid = threadIdx.x;
+    const int q = tid & (C - 1);
+    const int t = tid >> LOG2C;
+    const long long tile = blockIdx.x;
+    const long long b = tile / p.tiles_per_item;
+    const int r = (int)(tile - b * p.tiles_per_item);
+    const int ra = r / p.G, rg = r - ra * p.G;
+    const unsigned flags = p.flags;
+
+    long long item = b;
+    long long s_xoff = (long long)ra * p.s_SA + (long long)rg * p.s_SG;
+    long long d_xoff = (long long)ra * p.d_SA + (long long)rg * p.d_SG;
+    if (flags & PF_Q_IS_BATCH) {
+        item = b * C + q;
+    } else {
+        s_xoff += q * p.s_q;
+        d_xoff += q * p.d_q;
+    }
+    const bool valid = item < p.batch;
+    const unsigned col = (unsigned)(rg * C + q);       // column offset inside the [L][B] sub-matrix
+
+    cplx v[16];
+    if (valid) {
+        const cplx *src = p.src + item * p.src_batch_stride;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int i = t + m * T;
+            const int pos = (flags & PF_IN_REV) ? rev_bits(i, LOG2L) : i;
+            const long long off = s_xoff + (long long)pos * p.s_i;
+            cplx x = src[off];
+            if (flags & PF_RIFFT_PRE) {
+                cplx y = src[off + p.aux_off];
+                cplx w = ldg_c(p.r2tw + off);
+                x = cadd(cadd(x, y), cmul(csub(x, y), w));
+            }
+            if (flags & PF_SCALE) x = cscale(x, p.scale);
+            if (flags & (PF_WIN_REAL | PF_WIN_CPLX)) {
+                long long widx = off;
+                if (flags & PF_WIN_REV) widx = rev_bits64(off, p.lgN);
+                widx += item * p.window_batch_stride;
+                if (flags & PF_WIN_REAL) x = cscale(x, __ldg(reinterpret_cast<const double *>(p.window) + widx));
+                else x = cmul(x, ldg_c(reinterpret_cast<const cplx *>(p.window) + widx));
+            }
+            if (flags & PF_CONJ_IN) x = cconj(x);
+            if (flags & PF_TW_LOAD) x = cmul(x, big_twiddle(p, (unsigned long long)i * col));
+            v[m] = x;
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; m++) v[m] = make_double2(0.0, 0.0);
+    }
+
+    Stages<LOG2L, 0, 0>::run(v, sm, p.stage_tw, t, q);
+
+    if (valid) {
+        cplx *dst = p.dst + item * p.dst_batch_stride;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int k = t + m * T;
+            cplx y = v[m];
+            if (flags & PF_TW_STORE) y = cmul(y, big_twiddle(p, (unsigned long long)k * col));
+            if (flags & PF_CONJ_OUT) y = cconj(y);
+            const int pos = (flags & PF_OUT_REV) ? rev_bits(k, LOG2L) : k;
+            dst[d_xoff + (long long)pos * p.d_i] = y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// n <= 8: one thread per transform
+// ------------------------------------------------------------------------------------------
+struct TinyParams {
+    const cplx *src; cplx *dst;
+    long long src_batch_stride, dst_batch_stride, batch;
+    int lgn;
+    unsigned flags;
+    double scale;
+    const void *window;
+    long long window_batch_stride;
+    const cplx *r2tw;
+};
+
+__global__ void __launch_bounds__(256) fft_tiny_kernel(const TinyParams p) {
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= p.batch) return;
+    const int n = 1 << p.lgn;
+    const cplx *src = p.src + item * p.src_batch_stride;
+    cplx *dst = p.dst + item * p.dst_batch_stride;
+    cplx v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i < n) {
+            const int pos = (p.flags & PF_IN_REV) ? rev_bits(i, p.lgn) : i;
+            cplx x = src[pos];
+            if (p.flags & PF_RIFFT_PRE) {
+                cplx y = src[pos + n];
+                x = cadd(cadd(x, y), cmul(csub(x, y), ldg_c(p.r2tw + pos)));
+            }
+            if (p.flags & PF_SCALE) x = cscale(x, p.scale);
+            if (p.flags & (PF_WIN_REAL | PF_WIN_CPLX)) {
+                long long widx = pos;
+                if (p.flags & PF_WIN_REV) widx = rev_bits(pos, p.lgn);
+                widx += item * p.window_batch_stride;
+                if (p.flags & PF_WIN_REAL) x = cscale(x, __ldg(reinterpret_cast<const double *>(p.window) + widx));
+                else x = cmul(x, ldg_c(reinterpret_cast<const cplx *>(p.window) + widx));
+            }
+            if (p.flags & PF_CONJ_IN) x = cconj(x);
+            v[i] = x;
+        } else v[i] = make_double2(0.0, 0.0);
+    }
+    if (p.lgn == 1) Radix<2>::run(v);
+    else if (p.lgn == 2) Radix<4>::run(v);
+    else if (p.lgn == 3) Radix<8>::run(v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (k < n) {
+            cplx y = v[k];
+            if (p.flags & PF_CONJ_OUT) y = cconj(y);
+            const int pos = (p.flags & PF_OUT_REV) ? rev_bits(k, p.lgn) : k;
+            dst[pos] = y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone bit reversal (bit-reversal.lisp:146-252): out[i] = in[rev_w(i)], in place allowed.
+// Index = [hi:A][mid][lo:A]; a CTA exchanges the (2^A x 2^A) tiles of mid and rev(mid) through
+// shared memory, so both its global reads and writes are 2^A contiguous elements.
+// ------------------------------------------------------------------------------------------
+template <typename E, int A>
+__global__ void __launch_bounds__(256) bitrev_tiled_kernel(const E *src, E *dst, int w, long long src_stride,
+                                                           long long dst_stride, int pairs_per_item,
+                                                           const unsigned *pair_table) {
+    constexpr int S = 1 << A;
+    __shared__ E tileA[S][S + 1];
+    __shared__ E tileB[S][S + 1];
+    const long long item = blockIdx.x / pairs_per_item;
+    const int pr = blockIdx.x - item * pairs_per_item;
+    const unsigned mu = pair_table[2 * pr], mu2 = pair_table[2 * pr + 1];
+    const E *s = src + item * src_stride;
+    E *d = dst + item * dst_stride;
+    const int hs = w - A;                   // shift of the hi field
+    const int tx = threadIdx.x & (S - 1), ty0 = threadIdx.x >> A;
+    constexpr int ROWS = 256 / S;
+    // read tile(mu2) into A and (if distinct) tile(mu) into B: element (hi, lo)
+    for (int hi = ty0; hi < S; hi += ROWS) {
+        tileA[hi][tx] = s[((long long)hi << hs) + ((long long)mu2 << A) + tx];
+        if (mu != mu2) tileB[hi][tx] = s[((long long)hi << hs) + ((long long)mu << A) + tx];
+    }
+    __syncthreads();
+    // out[hi, mu, lo] = in[rev lo, mu2, rev hi]
+    const int rlo = rev_bits(tx, A);
+    for (int hi = ty0; hi < S; hi += ROWS) {
+        const int rhi = rev_bits(hi, A);
+        d[((long long)hi << hs) + ((long long)mu << A) + tx] = tileA[rlo][rhi];
+        if (mu != mu2) d[((long long)hi << hs) + ((long long)mu2 << A) + tx] = tileB[rlo][rhi];
+    }
+}
+
+// small sizes: one CTA per item, whole vector through shared memory (n <= 2048 elements)
+template <typename E>
+__global__ void __launch_bounds__(256) bitrev_small_kernel(const E *src, E *dst, int w, long long src_stride,
+                                                           long long dst_stride) {
+    NAPA_DYN_SMEM(E, sm);
+    const int n = 1 << w;
+    const E *s = src + (long long)blockIdx.x * src_stride;
+    E *d = dst + (long long)blockIdx.x * dst_stride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = s[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = rev_bits(i, w);
+        d[i] = sm[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// real wrappers
+// ------------------------------------------------------------------------------------------
+// rfft epilogue = fft-swizzled-reals split (real.lisp:16-30) + final radix-2 (real.lisp:128-134),
+// in place on dst (n complex per item) whose first half holds Z = FFT_{n/2}(packed reals).
+// One thread owns the index pair (i, h-i) and the four cells it touches.
+__global__ void __launch_bounds__(256) rfft_post_kernel(cplx *dst, long long dst_stride, long long batch, long long n,
+                                                        const cplx *__restrict__ r2tw) {
+    const long long h = n >> 1;
+    const long long per = (h >> 1) + 1;                  // i = 0 .. h/2
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per * batch) return;
+    const long long item = gid / per, i = gid - item * per;
+    cplx *d = dst + item * dst_stride;
+    if (i == 0) {
+        cplx z = d[0];                                    // E0 = re, O0 = im, tw[0] = 1
+        d[0] = make_double2(z.x + z.y, 0.0);
+        d[h] = make_double2(z.x - z.y, 0.0);
+        return;
+    }
+    const long long j = h - i;
+    cplx x = d[i], y = d[j];
+    // O_i = .5*(conj(swap x) + swap y), O_j = .5*(conj(swap y) + swap x); E = Z - i*O
+    cplx oi = make_double2(0.5 * (x.y + y.y), 0.5 * (y.x - x.x));
+    cplx oj = make_double2(0.5 * (y.y + x.y), 0.5 * (x.x - y.x));
+    cplx ei = make_double2(x.x + oi.y, x.y - oi.x);
+    cplx ej = make_double2(y.x + oj.y, y.y - oj.x);
+    cplx ti = cmul(oi, ldg_c(r2tw + i));
+    d[i] = cadd(ei, ti); d[i + h] = csub(ei, ti);
+    if (j != i) {
+        cplx tj = cmul(oj, ldg_c(r2tw + j));
+        d[j] = cadd(ej, tj); d[j + h] = csub(ej, tj);
+    }
+}
+
+// %2rfft epilogue (real.lisp:16-30 on a 2n array): dst[0..n) = FFT(v1), dst[n..2n) = FFT(v2)
+__global__ void __launch_bounds__(256) split2_post_kernel(cplx *dst, long long dst_stride, long long batch, long long n) {
+    const long long per = (n >> 1) + 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per * batch) return;
+    const long long item = gid / per, i = gid - item * per;
+    cplx *d = dst + item * dst_stride;
+    if (i == 0) {
+        cplx z = d[0];
+        d[n] = make_double2(z.y, 0.0);
+        d[0] = make_double2(z.x, 0.0);
+        return;
+    }
+    const long long j = n - i;
+    cplx x = d[i], y = d[j];
+    cplx oi = make_double2(0.5 * (x.y + y.y), 0.5 * (y.x - x.x));
+    cplx oj = make_double2(0.5 * (y.y + x.y), 0.5 * (x.x - y.x));
+    d[n + i] = oi;
+    d[2 * n - i] = oj;
+    d[i] = make_double2(x.x + oi.y, x.y - oi.x);
+    if (j != i) d[j] = make_double2(y.x + oj.y, y.y - oj.x);
+    else d[i] = make_double2(y.x + oj.y, y.y - oj.x);     // reference writes vec[h-i] last
+}
+
+// pack two real vectors into one complex vector (real.lisp:45-47)
+__global__ void __launch_bounds__(256) zip2_kernel(const double *v1, const double *v2, cplx *dst, long long n,
+                                                   long long batch, long long v_stride, long long dst_stride) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * batch) return;
+    const long long item = gid / n, i = gid - item * n;
+    dst[item * dst_stride + i] = make_double2(v1[item * v_stride + i], v2[item * v_stride + i]);
+}
+
+// pointwise helpers used by device-resident pipelines (convolution building block, tests)
+__global__ void __launch_bounds__(256) cmul_pointwise_kernel(cplx *a, const cplx *__restrict__ b, long long n,
+                                                             long long batch, long long b_stride) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * batch) return;
+    const long long item = gid / n, i = gid - item * n;
+    a[gid] = cmul(a[gid], b[item * b_stride + i]);
+}
+
+}  // namespace napa

@@ -1,0 +1,78 @@
+// cuda_emul.cpp -- fiber scheduler behind tests/emul/cuda_emul.h (TEST-ONLY, see that header).
+#include "cuda_emul.h"
+
+#include <stdio.h>
+
+namespace napa_emul {
+
+uint3_ threadIdx_, blockIdx_;
+dim3 blockDim_, gridDim_;
+unsigned char *dyn_smem = nullptr;
+
+namespace {
+constexpr size_t kStack = 96 * 1024;
+enum FState { READY, AT_BARRIER, DONE };
+struct Fiber { ucontext_t ctx; FState st; unsigned char *stack; };
+std::vector<Fiber> fibers;
+ucontext_t sched_ctx;
+int current = -1;
+const std::function<void()> *cur_body = nullptr;
+
+void trampoline() {
+    (*cur_body)();
+    fibers[current].st = DONE;
+    swapcontext(&fibers[current].ctx, &sched_ctx);
+}
+}  // namespace
+
+void syncthreads() {
+    fibers[current].st = AT_BARRIER;
+    swapcontext(&fibers[current].ctx, &sched_ctx);
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    const unsigned nthreads = block.x * block.y * block.z;
+    if (fibers.size() < nthreads) {
+        size_t old = fibers.size();
+        fibers.resize(nthreads);
+        for (size_t i = old; i < nthreads; i++) fibers[i].stack = (unsigned char *)malloc(kStack);
+    }
+    void *sm = nullptr;
+    if (posix_memalign(&sm, 128, smem ? smem : 16)) abort();
+    dyn_smem = (unsigned char *)sm;
+    blockDim_ = block; gridDim_ = grid;
+    cur_body = &body;
+    for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+    for (unsigned bx = 0; bx < grid.x; bx++) {
+        blockIdx_ = { bx, by, bz };
+        for (unsigned t = 0; t < nthreads; t++) {
+            Fiber &f = fibers[t];
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = kStack;
+            f.ctx.uc_link = &sched_ctx;
+            makecontext(&f.ctx, trampoline, 0);
+            f.st = READY;
+        }
+        for (;;) {
+            unsigned live = 0, waiting = 0;
+            for (unsigned t = 0; t < nthreads; t++) {
+                Fiber &f = fibers[t];
+                if (f.st == DONE) continue;
+                current = (int)t;
+                threadIdx_ = { t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
+                f.st = READY;
+                swapcontext(&sched_ctx, &f.ctx);
+                if (f.st != DONE) { live++; if (f.st == AT_BARRIER) waiting++; }
+            }
+            if (live == 0) break;
+            if (waiting != live) { fprintf(stderr, "napa_emul: barrier divergence\n"); abort(); }
+        }
+    }
+    free(sm);
+    dyn_smem = nullptr;
+    cur_body = nullptr;
+}
+
+}  // namespace napa_emul

@@ -1,0 +1,101 @@
+"""CPU tier: the shipped planner + kernel source (napa_fft3_b200/csrc) compiled against the
+test-only CUDA emulation, driven through the same C ABI and Python host as on the GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import parity_suite as S  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def napa():
+    from emul.build_emul import build
+    from napa_fft3_b200 import Binding, NapaFFT
+    b = Binding(build())
+    b.init(0)
+    return NapaFFT(b)
+
+
+SIZES = [1 << k for k in range(0, 15)]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_fft_all_options(napa, n):
+    for in_order in (True, False):
+        for scale, wt in ((None, None), (True, "real"), ("sqrt", "complex")):
+            S.check_fft(napa, n, in_order, scale, wt)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_ifft_all_options(napa, n):
+    for in_order in (True, False):
+        for scale, wt in ((True, None), (None, "real"), ("sqrt", "complex")):
+            S.check_ifft(napa, n, in_order, scale, wt)
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(1, 15)])
+def test_layout_bit_exact(napa, n):
+    S.check_layout_bit_exact(napa, n)
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(0, 16)])
+def test_bit_reverse(napa, n):
+    S.check_bit_reverse(napa, n)
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 32, 1024, 1 << 14])
+def test_offsets_exact(napa, n):
+    S.check_offsets_exact(napa, n)
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(1, 16)])
+def test_real(napa, n):
+    for scale in (None, True, "sqrt"):
+        S.check_real(napa, n, scale)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 64, 1 << 13])
+def test_2rfft(napa, n):
+    if n >= 2:
+        S.check_2rfft(napa, n)
+
+
+@pytest.mark.parametrize("n", [4, 64, 1024])
+def test_ergun(napa, n):
+    S.check_ergun(napa, n, True)
+    S.check_ergun(napa, n, False)
+
+
+def test_readme_kats(napa):
+    S.check_readme_kats(napa)
+
+
+def test_dst_rules(napa):
+    S.check_dst_rules(napa)
+
+
+def test_windowed(napa):
+    S.check_windowed(napa)
+
+
+def test_window_functions(napa):
+    S.check_window_functions(napa)
+
+
+def test_batch_and_stride(napa):
+    """new export: many transforms per call (rows), incl. a per-batch window"""
+    from oracle import napa_oracle as O
+    x = np.stack([S.rand_c(100 + i, 256) for i in range(19)])
+    w = np.stack([S.rand_r(200 + i, 256, 1, 2) for i in range(19)])
+    got = napa.fft_batch(x.copy(), in_order=False, scale="sqrt", window=w)
+    for i in range(19):
+        assert S.nre(got[i], O.fft(x[i], in_order=False, scale="sqrt", window=w[i])) <= S.tol(256)
+    r = np.stack([S.rand_r(300 + i, 512) for i in range(5)])
+    spec = napa.rfft_batch(r)
+    for i in range(5):
+        assert S.nre(spec[i], O.rfft(r[i])) <= S.tol(512)
+    back = napa.rifft_batch(spec)
+    assert S.nre(back, r) < 1e-12

@@ -1,0 +1,168 @@
+"""GPU tier (-m gpu): the product library (sm_100a kernels) through the C ABI vs the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import parity_suite as S  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def napa():
+    import napa_fft3_b200 as P
+    from napa_fft3_b200.build import build
+    build()
+    P.default_binding()          # raises if the CUDA library or the GPU is missing: no fallback
+    return P._default
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(0, 21)])
+def test_fft_all_options(napa, n):
+    for in_order in (True, False):
+        for scale, wt in ((None, None), (True, "real"), ("sqrt", "complex")):
+            S.check_fft(napa, n, in_order, scale, wt)
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(0, 21)])
+def test_ifft_all_options(napa, n):
+    for in_order in (True, False):
+        for scale, wt in ((True, None), (None, "real"), ("sqrt", "complex")):
+            S.check_ifft(napa, n, in_order, scale, wt)
+
+
+@pytest.mark.parametrize("n", [1 << 22, 1 << 24, 1 << 25])
+def test_large_single(napa, n):
+    S.check_fft(napa, n, True, None, None)
+    S.check_fft(napa, n, False, "sqrt", "real")
+    S.check_ifft(napa, n, False, True, "complex")
+    S.check_ifft(napa, n, True, True, None)
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(1, 21)])
+def test_layout_bit_exact(napa, n):
+    S.check_layout_bit_exact(napa, n)
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(0, 23)])
+def test_bit_reverse(napa, n):
+    S.check_bit_reverse(napa, n)
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 32, 1024, 1 << 14, 1 << 18])
+def test_offsets_exact(napa, n):
+    S.check_offsets_exact(napa, n)
+
+
+@pytest.mark.parametrize("n", [1 << k for k in range(1, 21)])
+def test_real(napa, n):
+    for scale in (None, True, "sqrt"):
+        S.check_real(napa, n, scale)
+
+
+@pytest.mark.parametrize("n", [2, 4, 64, 1 << 13, 1 << 17])
+def test_2rfft(napa, n):
+    S.check_2rfft(napa, n)
+
+
+@pytest.mark.parametrize("n", [4, 64, 1024, 1 << 16])
+def test_ergun(napa, n):
+    S.check_ergun(napa, n, True)
+    S.check_ergun(napa, n, False)
+
+
+def test_readme_kats(napa):
+    S.check_readme_kats(napa)
+
+
+def test_dst_rules(napa):
+    S.check_dst_rules(napa)
+
+
+def test_windowed(napa):
+    S.check_windowed(napa)
+    S.check_windowed(napa, 1 << 12)
+
+
+def test_window_functions(napa):
+    S.check_window_functions(napa)
+
+
+def test_batched_configs_vs_oracle(napa):
+    """BASELINE configs at reduced batch, every item compared with the oracle.
+    C2: windowed (Hann) fft -> ifft :scale :inv, 2^16; C3: fft :in-order nil -> ifft with complex
+    window (convolution building block), 2^20; C4: rfft -> rifft, 2^14."""
+    import napa_fft3_b200 as P
+    from oracle import napa_oracle as O
+    n, B = 1 << 16, 24
+    x = np.stack([S.rand_c(1002 + i, n) for i in range(B)])
+    hann = napa.window_vector(P.hann, n)
+    spec = napa.fft_batch(x.copy(), window=hann)
+    back = napa.fft_batch(spec.copy(), direction=-1, scale="inv")
+    for i in range(B):
+        want = O.fft(x[i], window=hann)
+        assert S.nre(spec[i], want) <= S.tol(n)
+        assert S.nre(back[i], O.ifft(want.copy(), scale=True)) <= S.tol(n)
+    n, B = 1 << 20, 6
+    x = np.stack([S.rand_c(1003 + i, n) for i in range(B)])
+    h = napa.fft(S.rand_c(999, n), in_order=False)
+    spec = napa.fft_batch(x.copy(), in_order=False)
+    conv = napa.fft_batch(spec.copy(), direction=-1, in_order=False, scale="inv", window=h)
+    for i in range(B):
+        want = O.fft(x[i], in_order=False)
+        assert S.nre(spec[i], want) <= S.tol(n)
+        assert S.nre(conv[i], O.ifft(want.copy(), in_order=False, scale=True, window=h)) <= S.tol(n)
+    n, B = 1 << 14, 64
+    r = np.stack([S.rand_r(1004 + i, n) for i in range(B)])
+    spec = napa.rfft_batch(r)
+    back = napa.rifft_batch(spec.copy())
+    for i in range(B):
+        want = O.rfft(r[i])
+        assert S.nre(spec[i], want) <= S.tol(n)
+        assert S.nre(back[i], O.rifft(want.copy())) <= S.tol(n)
+
+
+def test_full_size_properties_device_resident(napa):
+    """BASELINE full sizes through the device-resident entry points, checked by size-independent
+    properties: round trip, linearity, Parseval, and a sample of items against the oracle."""
+    import torch
+    import napa_fft3_b200 as P
+    from oracle import napa_oracle as O
+    b = P.default_binding()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(1005)
+    for n, B, in_order in ((1 << 16, 512, True), (1 << 20, 64, False), (1 << 10, 4096, True)):
+        x = torch.view_as_complex(torch.rand((B, n, 2), dtype=torch.float64, device=dev, generator=g) * 2 - 1).contiguous()
+        y = torch.empty_like(x)
+        st = torch.cuda.current_stream().cuda_stream
+        b.c2c_dev(x.data_ptr(), y.data_ptr(), n, B, n, 1, 0, int(in_order), None, 0, 0, st)
+        torch.cuda.synchronize()
+        # Parseval: sum |X|^2 = n sum |x|^2
+        ex, ey = (x.abs() ** 2).sum(dim=1), (y.abs() ** 2).sum(dim=1)
+        assert torch.max(torch.abs(ey / (n * ex) - 1)).item() < 1e-12
+        # oracle on a few items
+        for i in (0, B // 2, B - 1):
+            want = O.fft(x[i].cpu().numpy(), in_order=in_order)
+            assert S.nre(y[i].cpu().numpy(), want) <= S.tol(n)
+        # linearity: F(a + 2b) = F(a) + 2 F(b)
+        z = torch.empty_like(x)
+        comb = (x + 2 * x.roll(1, 0)).contiguous()
+        b.c2c_dev(comb.data_ptr(), z.data_ptr(), n, B, n, 1, 0, int(in_order), None, 0, 0, st)
+        torch.cuda.synchronize()
+        ref = y + 2 * y.roll(1, 0)
+        assert (torch.linalg.norm(z - ref) / torch.linalg.norm(ref)).item() < 1e-14 * np.log2(n) * 10
+        # round trip in place
+        b.c2c_dev(y.data_ptr(), y.data_ptr(), n, B, n, -1, 1, int(in_order), None, 0, 0, st)
+        torch.cuda.synchronize()
+        assert (torch.linalg.norm(y - x) / torch.linalg.norm(x)).item() <= S.tol(n)
+
+
+def test_launch_counter_moves(napa):
+    import napa_fft3_b200 as P
+    b = P.default_binding()
+    before = b.launch_count()
+    napa.fft(np.arange(1024, dtype=np.complex128))
+    assert b.launch_count() > before
