@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of napa-fft3-b200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+
+A STEP is one pass of the hot path over one batch of synthetic input already resident in HBM.
+Default workload (N = 1) is BASELINE.json configs[1] ("c2"): 4096 x 2^16 complex doubles,
+windowed-fft (shared Hann window, :in-order t) followed by ifft :scale :inv (:in-order t).
+Metric: FP64 complex FFT GFLOP/s = 5 N log2 N per transform / time (BASELINE.json `metric`).
+N > 1: one process per GPU (torchrun), the batch is sharded with no data-path collective
+(weak scaling: every GPU gets the full per-GPU batch); time = max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, batch, description)
+    "c1": (1 << 10, 1, "fft n=2^10 single transform, :in-order t :scale nil"),
+    "c2": (1 << 16, 4096, "4096 x 2^16 complex doubles: windowed-fft (shared Hann, :in-order t) -> ifft :scale :inv"),
+    "c3": (1 << 20, 1024, "1024 x 2^20: fft :in-order nil -> ifft :in-order nil :window H (shared complex filter)"),
+    "c4": (1 << 14, 8192, "8192 x 2^14 reals: rfft :scale nil -> rifft :scale t"),
+}
+
+
+def flops_per_step(wl):
+    n, batch, _ = WORKLOADS[wl]
+    lg = np.log2(n)
+    if wl == "c1":
+        return 5.0 * n * lg * batch
+    if wl == "c4":
+        return 2 * 2.5 * n * lg * batch
+    return 2 * 5.0 * n * lg * batch
+
+
+def algorithmic_bytes_per_step(wl):
+    """c2c 32 N B per transform (+ shared window once), rfft/rifft 24 N."""
+    n, batch, _ = WORKLOADS[wl]
+    if wl == "c1":
+        return 32.0 * n * batch
+    if wl == "c4":
+        return 2 * 24.0 * n * batch
+    win = 8.0 * n if wl == "c2" else 16.0 * n
+    return 2 * 32.0 * n * batch + win
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle (C restatement of Napa-FFT3; SBCL is not available)
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_step(wl, items, threads, state):
+    """One bounded step of the same workload on the host cores, batch-parallel over `threads`."""
+    from oracle import napa_oracle as O
+    n = WORKLOADS[wl][0]
+    data, win = state["data"], state["win"]
+
+    def work(lo, hi):
+        for i in range(lo, hi):
+            if wl == "c1":
+                O.fft(data[i].copy())
+            elif wl == "c2":
+                y = O.fft(data[i].copy(), window=win)
+                O.ifft(y, dst=y, scale=True)
+            elif wl == "c3":
+                y = O.fft(data[i].copy(), in_order=False)
+                O.ifft(y, dst=y, in_order=False, scale=True, window=win)
+            else:
+                y = O.rfft(data[i])
+                O.rifft(y)
+    per = (items + threads - 1) // threads
+    ts = [threading.Thread(target=work, args=(t * per, min(items, (t + 1) * per))) for t in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+
+
+def cpu_oracle_state(wl, items):
+    from oracle import napa_oracle as O
+    n = WORKLOADS[wl][0]
+    O.lib().napa_oracle_warm(n)
+    rng = np.random.Generator(np.random.Philox(1002))
+    if wl == "c4":
+        data = rng.uniform(-1, 1, (items, n))
+        O.rifft(O.rfft(data[0]))
+        win = None
+    else:
+        data = rng.uniform(-1, 1, (items, n)) + 1j * rng.uniform(-1, 1, (items, n))
+        win = O.window_vector("hann", n) if wl == "c2" else (O.fft(data[0], in_order=False) if wl == "c3" else None)
+    return {"data": data, "win": win}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    n, batch, desc = WORKLOADS[wl]
+    threads = os.cpu_count() or 1
+    items = min(batch, (64 if n <= (1 << 16) else 4) * threads)      # ~1 s of host work per step
+    state = cpu_oracle_state(wl, items)
+    for _ in range(args.warmup):
+        cpu_oracle_step(wl, items, threads, state)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_step(wl, items, threads, state)
+    dt = (time.perf_counter() - t0) / args.steps
+    gflops = flops_per_step(wl) * (items / batch) / dt / 1e9
+    sample = "%d of %d transforms per step on %d threads (oracle: C restatement of Napa-FFT3, SBCL unavailable)" % (items, batch, threads)
+    line = {
+        "impl": "reference", "metric": "fp64_complex_fft_gflops", "value": gflops, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch},
+        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        return self.summarise(t_begin, t_end)
+
+    def summarise(self, t_begin, t_end):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t_begin or ts > t_end + 0.2:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax = float(parts[2]); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="napa", choices=["napa", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "napa" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import napa_fft3_b200 as napa
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ["NAPAFFT_DEVICE"] = str(local)
+    b = napa.default_binding()                      # CUDA library or bust
+
+    wl = args.workload
+    n, batch, desc = WORKLOADS[wl]
+    stream = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device=dev); g.manual_seed(1002 + rank)
+
+    # ---- synthetic inputs resident in HBM (re, im ~ U[-1,1), test-support.lisp:19-25) ----
+    if wl == "c4":
+        x = (torch.rand((batch, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1)
+        y = torch.empty((batch, n), dtype=torch.complex128, device=dev)
+        z = torch.empty((batch, n), dtype=torch.float64, device=dev)
+        win = None
+    else:
+        x = torch.view_as_complex(torch.rand((batch, n, 2), dtype=torch.float64, device=dev, generator=g) * 2 - 1).contiguous()
+        y = torch.empty_like(x)
+        z = torch.empty_like(x)
+        if wl == "c2":
+            win = torch.from_numpy(napa.window_vector(napa.hann, n)).to(dev)      # (hann i n), windowing.lisp:10
+        elif wl == "c3":
+            hw = torch.view_as_complex(torch.rand((n, 2), dtype=torch.float64, device=dev, generator=g) * 2 - 1).contiguous()
+            win = torch.empty_like(hw)
+            b.c2c_dev(hw.data_ptr(), win.data_ptr(), n, 1, n, 1, 0, 0, None, 0, 0, stream)   # H = fft h :in-order nil
+        else:
+            win = None
+    wp = win.data_ptr() if win is not None else None
+
+    def step():
+        if wl == "c1":
+            b.c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, n, 1, 0, 1, None, 0, 0, stream)
+        elif wl == "c2":
+            b.c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, n, 1, 0, 1, wp, 1, 0, stream)
+            b.c2c_dev(y.data_ptr(), z.data_ptr(), n, batch, n, -1, 1, 1, None, 0, 0, stream)
+        elif wl == "c3":
+            b.c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, n, 1, 0, 0, None, 0, 0, stream)
+            b.c2c_dev(y.data_ptr(), z.data_ptr(), n, batch, n, -1, 1, 0, wp, 2, 0, stream)
+        else:
+            b.rfft_dev(x.data_ptr(), y.data_ptr(), n, batch, 0, stream)
+            b.rifft_dev(y.data_ptr(), z.data_ptr(), n, batch, 1, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    t_warm = time.perf_counter()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = b.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t_end = time.perf_counter()
+    launches = b.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_begin, t_end)
+    clocks["window"] = "timed region"
+    if not clocks.get("samples") or clocks["samples"] < 3:
+        clocks = sampler.summarise(t_warm, t_end)
+        clocks["window"] = "warm-up + timed region (timed region shorter than 3 samples at 100 ms)"
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = flops_per_step(wl) * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- quick self-check of the timed path against the oracle (not timed) ----
+    parity = None
+    if rank == 0:
+        from oracle import napa_oracle as O
+        i = batch // 2
+        if wl == "c4":
+            want = O.rifft(O.rfft(x[i].cpu().numpy()))
+        elif wl == "c2":
+            want = O.ifft(O.fft(x[i].cpu().numpy(), window=win.cpu().numpy()), scale=True)
+        elif wl == "c3":
+            want = O.ifft(O.fft(x[i].cpu().numpy(), in_order=False), in_order=False, scale=True, window=win.cpu().numpy())
+        else:
+            want = O.fft(x[i].cpu().numpy())
+        got = (y if wl == "c1" else z)[i].cpu().numpy()
+        parity = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+
+    # ---- roofline of the dominant kernel (fft_pass_kernel) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = algorithmic_bytes_per_step(wl) / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(wl)
+    except Exception:
+        pass
+    launches_per_step = launches / max(args.steps, 1)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "napa::fft_pass_kernel<LOG2L>",
+                "algorithmic_bytes_per_launch": algorithmic_bytes_per_step(wl) / max(launches_per_step, 1),
+                "avg_launch_ms": ms_per_step / max(launches_per_step, 1),
+                "frac_of_nominal_8000": achieved / 8000.0}
+
+    # ---- e2e: the same step through the host-buffer C ABI (pinned host arrays, PCIe inside) ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, torch, dist, napa, b, wl, world, dev, win)
+        except Exception as ex:  # report, never fake
+            e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:200]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        items = min(batch, 2 * threads)
+        st = cpu_oracle_state(wl, items)
+        cpu_oracle_step(wl, items, threads, st)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 8.0 and reps < 50:
+            cpu_oracle_step(wl, items, threads, st); reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": flops_per_step(wl) * (items / batch) / dt / 1e9, "unit": "GFLOP/s", "cores": threads,
+                        "kind": "port",
+                        "sample": "%d of %d transforms per step, %d reps, batch-parallel over %d threads; oracle = C "
+                                  "restatement of Napa-FFT3 (SBCL unavailable)" % (items, batch, reps, threads)}
+
+    if rank == 0:
+        line = {
+            "metric": "fp64_complex_fft_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch,
+                       "l2_policy": "inputs_exceed_l2 (%.1f GiB per array per GPU)" % (x.numel() * x.element_size() / 2**30),
+                       "sharding": "batch-sharded, no collective" if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "parity_nre_vs_oracle": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dist, napa, b, wl, world, dev, win):
+    """Same step through the reference-facing host-pointer entry points: inputs and outputs are
+    page-locked HOST arrays, every step pays H2D + D2H inside the timed region."""
+    n, batch, _ = WORKLOADS[wl]
+    rng = np.random.Generator(np.random.Philox(2002))
+    if wl == "c4":
+        hx = torch.empty((batch, n), dtype=torch.float64, pin_memory=True)
+        hy = torch.empty((batch, n), dtype=torch.complex128, pin_memory=True)
+        hz = torch.empty((batch, n), dtype=torch.float64, pin_memory=True)
+        hx.numpy()[:] = rng.uniform(-1, 1, (batch, n))
+    else:
+        hx = torch.empty((batch, n), dtype=torch.complex128, pin_memory=True)
+        hy = torch.empty((batch, n), dtype=torch.complex128, pin_memory=True)
+        hz = hy
+        v = hx.numpy().view(np.float64)
+        chunk = max(1, (1 << 24) // n)
+        for i in range(0, batch, chunk):
+            v[i:i + chunk] = rng.uniform(-1, 1, v[i:i + chunk].shape)
+    hwin = win.cpu().numpy() if win is not None else None
+    x, y, z = hx.numpy(), hy.numpy(), hz.numpy()
+
+    def step():
+        if wl == "c1":
+            napa.fft_batch(x, out=y)
+        elif wl == "c2":
+            napa.fft_batch(x, window=hwin, out=y)
+            napa.fft_batch(y, direction=-1, scale="inv", out=z)
+        elif wl == "c3":
+            napa.fft_batch(x, in_order=False, out=y)
+            napa.fft_batch(y, direction=-1, in_order=False, scale="inv", window=hwin, out=z)
+        else:
+            napa.rfft_batch(x, out=y)
+            napa.rifft_batch(y, out=z)
+
+    step()                                           # warm the staging buffers
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    dt /= args.e2e_steps
+    if wl == "c4":
+        h2d, d2h = (8 + 16) * n * batch, (16 + 8) * n * batch
+    elif wl == "c1":
+        h2d, d2h = 16 * n * batch, 16 * n * batch
+    else:
+        h2d = 2 * 16 * n * batch + (hwin.nbytes if hwin is not None else 0)
+        d2h = 2 * 16 * n * batch
+    return {"value": flops_per_step(wl) * world / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+            "api": "napafft_c2c / napafft_rfft / napafft_rifft on page-locked host arrays"}
+
+
+if __name__ == "__main__":
+    main()
