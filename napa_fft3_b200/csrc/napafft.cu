@@ -73,8 +73,14 @@ struct State {
     void *pinned[2] = {}; size_t pinned_bytes = 0;
     void *dbuf[2] = {}; size_t dbuf_bytes = 0;
     void *dwin = nullptr; size_t dwin_bytes = 0;
-    size_t chunk_bytes = 32u << 20;
+    size_t chunk_bytes = 32u << 20;       // per-launch chunk of the multi-launch fallback path
+    size_t pipe_chunk_bytes = 8u << 20;   // chunk of the persistent pipeline
+    int pipe_lag = 3;                     // phases between the two passes of a chunk
+    bool use_pipeline = true;
     bool attrs_set = false;
+    int num_sms = 148;
+    std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream ticket/done block
+    int *h_error = nullptr, *d_error = nullptr;                             // mapped error flag
 };
 static State G;
 
@@ -111,13 +117,21 @@ static inline cplx unit_root(unsigned long long e, unsigned long long M) {
     return make_double2((double)c, (double)(-s));
 }
 
+// Table uploads happen once per table.  cudaMemcpy from pageable memory may return before the DMA
+// has landed and does not order against cudaStreamNonBlocking streams, so fence explicitly.
+static int upload_table(void *dev, const void *host, size_t bytes) {
+    CU(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    return NAPA_OK;
+}
+
 static int ensure_stage_tw(int l) {
     if (G.stage_tw[l]) return NAPA_OK;
     size_t L = (size_t)1 << l;
     std::vector<cplx> h(L);
     for (size_t m = 0; m < L; m++) h[m] = unit_root(m, L);
     CU(cudaMalloc(&G.stage_tw[l], L * sizeof(cplx)));
-    CU(cudaMemcpy(G.stage_tw[l], h.data(), L * sizeof(cplx), cudaMemcpyHostToDevice));
+    OK(upload_table(G.stage_tw[l], h.data(), L * sizeof(cplx)));
     return NAPA_OK;
 }
 
@@ -133,8 +147,8 @@ static int ensure_big_tw(int lgM, BigTw *out) {
     for (size_t i = 0; i < nhi; i++) hi[i] = unit_root((unsigned long long)i << t.shift, M);
     CU(cudaMalloc(&t.lo, nlo * sizeof(cplx)));
     CU(cudaMalloc(&t.hi, nhi * sizeof(cplx)));
-    CU(cudaMemcpy(t.lo, lo.data(), nlo * sizeof(cplx), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(t.hi, hi.data(), nhi * sizeof(cplx), cudaMemcpyHostToDevice));
+    OK(upload_table(t.lo, lo.data(), nlo * sizeof(cplx)));
+    OK(upload_table(t.hi, hi.data(), nhi * sizeof(cplx)));
     G.big[lgM] = t;
     *out = t;
     return NAPA_OK;
@@ -162,7 +176,7 @@ static int ensure_r2tw(size_t n, int dir, cplx **out) {
     radix2_twiddle_host(n, dir, h.data());
     cplx *d;
     CU(cudaMalloc(&d, h.size() * sizeof(cplx)));
-    CU(cudaMemcpy(d, h.data(), h.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    OK(upload_table(d, h.data(), h.size() * sizeof(cplx)));
     G.r2tw[key] = d;
     *out = d;
     return NAPA_OK;
@@ -214,6 +228,69 @@ static int launch_pass(int l, PassParams &p, long long ntiles, cudaStream_t st) 
     if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
     pass_fn fn = pass_kernel(l);
     NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p);
+    g_launches++;
+    return NAPA_OK;
+}
+
+// persistent two-pass pipeline kernels: (first-executed digit, second digit)
+typedef void (*pipe_fn)(const napa::PipeParams);
+#define NAPA_PIPE_CASE(a, b) if (la == a && lb == b) return napa::fft_pipeline_kernel<a, b>;
+static pipe_fn pipe_kernel(int la, int lb) {
+    NAPA_PIPE_CASE(7, 7) NAPA_PIPE_CASE(7, 8) NAPA_PIPE_CASE(8, 7) NAPA_PIPE_CASE(8, 8)
+    NAPA_PIPE_CASE(8, 9) NAPA_PIPE_CASE(9, 8) NAPA_PIPE_CASE(9, 9) NAPA_PIPE_CASE(9, 10)
+    NAPA_PIPE_CASE(10, 9) NAPA_PIPE_CASE(10, 10) NAPA_PIPE_CASE(10, 11) NAPA_PIPE_CASE(11, 10)
+    NAPA_PIPE_CASE(10, 12) NAPA_PIPE_CASE(12, 10)
+    return nullptr;
+}
+
+static int ensure_counters(cudaStream_t st, size_t bytes, unsigned char **out) {
+    auto &slot = G.counters[st];
+    if (slot.second < bytes) {
+        if (slot.first) { CU(cudaDeviceSynchronize()); CU(cudaFree(slot.first)); }
+        size_t cap = std::max<size_t>(bytes, 64 << 10);
+        CU(cudaMalloc(&slot.first, cap));
+        slot.second = cap;
+    }
+    if (!G.h_error) {
+        CU(cudaHostAlloc((void **)&G.h_error, sizeof(int), cudaHostAllocMapped));
+        *G.h_error = 0;
+#ifdef NAPA_EMULATE
+        G.d_error = G.h_error;
+#else
+        CU(cudaHostGetDevicePointer((void **)&G.d_error, G.h_error, 0));
+#endif
+    }
+    *out = slot.first;
+    return NAPA_OK;
+}
+
+static int launch_pipeline(int la, int lb, napa::PipeParams &pp, cudaStream_t st) {
+    pipe_fn fn = pipe_kernel(la, lb);
+    if (!fn) return fail(NAPA_E_UNSUPPORTED, "no pipeline kernel for digits (%d, %d)", la, lb);
+    OK(ensure_stage_tw(la));
+    OK(ensure_stage_tw(lb));
+    pp.a.stage_tw = G.stage_tw[la];
+    pp.b.stage_tw = G.stage_tw[lb];
+    const size_t smem = std::max(napa::plan_smem_bytes(la), napa::plan_smem_bytes(lb));
+    static std::map<pipe_fn, int> occupancy;
+    auto it = occupancy.find(fn);
+    if (it == occupancy.end()) {
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, 256, smem));
+        if (nb < 1) return fail(NAPA_E_CUDA, "pipeline kernel does not fit on an SM");
+        it = occupancy.emplace(fn, nb).first;
+    }
+    const size_t cbytes = 16 + 2 * (size_t)pp.nchunks * sizeof(unsigned);
+    unsigned char *ctr;
+    OK(ensure_counters(st, cbytes, &ctr));
+    CU(cudaMemsetAsync(ctr, 0, cbytes, st));
+    pp.ticket = (unsigned long long *)ctr;
+    pp.done = (unsigned *)(ctr + 16);
+    pp.error = G.d_error;
+    const long long total_tiles = pp.items * pp.tiles_per_item * 2;
+    long long grid = std::min<long long>((long long)G.num_sms * it->second, total_tiles);
+    NAPA_LAUNCH(fn, (unsigned)grid, 256, smem, st, pp);
     g_launches++;
     return NAPA_OK;
 }
@@ -332,6 +409,62 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     chunk = std::min(chunk, batch);
 
     const bool natural = o.in_order != 0;
+    const bool can_pipe = G.use_pipeline && p == 2 && d[0] <= 12 && d[1] <= 12;
+    if (can_pipe) {
+        napa::PipeParams pp{};
+        size_t pchunk = std::max<size_t>(1, G.pipe_chunk_bytes / (n * sizeof(cplx)));
+        pchunk = std::min(pchunk, batch);
+        pp.items = (long long)batch; pp.chunk = (int)pchunk; pp.nchunks = (int)((batch + pchunk - 1) / pchunk);
+        pp.lag = std::max(1, G.pipe_lag);
+        pp.tiles_per_item = (long long)(n >> 12);
+        long long tpi;
+        if (natural) {
+            // A: column pass src -> scratch ring (+ inter-pass twiddle); B: row pass ring -> dst, transposed store
+            pp.slots = pp.lag + 2;
+            OK(ensure_scratch((size_t)pp.slots * pchunk * n * sizeof(cplx)));
+            BigTw bt; OK(ensure_big_tw(lg, &bt));
+            PassParams &p1 = pp.a, &p2 = pp.b;
+            pass_geometry(d, 0, p1, &tpi);
+            p1.src = src; p1.dst = G.scratch;
+            p1.src_batch_stride = (long long)sstride; p1.dst_batch_stride = (long long)n; p1.batch = (long long)batch;
+            p1.flags = napa::PF_TW_STORE | (inv ? napa::PF_CONJ_IN : 0);
+            p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << lg) - 1;
+            first_pass_fusions(p1, o, n, win_rev);
+            pass_geometry(d, 1, p2, &tpi);
+            p2.src = G.scratch; p2.dst = dst;
+            p2.src_batch_stride = (long long)n; p2.dst_batch_stride = (long long)dstride; p2.batch = (long long)batch;
+            p2.flags = inv ? napa::PF_CONJ_OUT : 0;
+            p2.d_SA = 1LL << napa::plan_log2c(d[1]); p2.d_SG = 0; p2.d_i = 1LL << d[0]; p2.d_q = 1;
+            pp.a_dst_is_ring = 1; pp.b_src_is_ring = 1;
+            OK(launch_pipeline(d[0], d[1], pp, st));
+        } else {
+            // bit-reversed layouts: in place on dst after the first pass, no scratch
+            pp.slots = 0;
+            const int sa = inv ? 1 : 0, sb = inv ? 0 : 1;      // DIT runs the digits last to first
+            BigTw bt; OK(ensure_big_tw(lg, &bt));
+            PassParams *ps[2] = { &pp.a, &pp.b };
+            const int order[2] = { sa, sb };
+            for (int step = 0; step < 2; step++) {
+                PassParams &q = *ps[step];
+                const int sdig = order[step];
+                pass_geometry(d, sdig, q, &tpi);
+                q.src = step == 0 ? src : dst; q.dst = dst;
+                q.src_batch_stride = (long long)(step == 0 ? sstride : dstride); q.dst_batch_stride = (long long)dstride;
+                q.batch = (long long)batch;
+                if (sdig == 0) {   // the column-like digit carries the twiddle
+                    q.tw_lo = bt.lo; q.tw_hi = bt.hi; q.tw_shift = bt.shift; q.tw_mask = (1ull << lg) - 1;
+                    q.flags |= inv ? napa::PF_TW_LOAD : napa::PF_TW_STORE;
+                }
+                q.flags |= inv ? napa::PF_IN_REV : napa::PF_OUT_REV;
+                if (inv && step == 0) q.flags |= napa::PF_CONJ_IN;
+                if (inv && step == 1) q.flags |= napa::PF_CONJ_OUT;
+                if (step == 0) first_pass_fusions(q, o, n, false);
+            }
+            OK(launch_pipeline(d[order[0]], d[order[1]], pp, st));
+        }
+        CU(cudaGetLastError());
+        return NAPA_OK;
+    }
     if (natural && p == 2) {
         // natural in -> natural out: column pass into L2-resident scratch, row pass stores transposed
         OK(ensure_scratch(chunk * n * sizeof(cplx)));
@@ -418,7 +551,7 @@ static int ensure_pairs(int w, PairTable *out) {
     PairTable t;
     t.count = (int)(h.size() / 2);
     CU(cudaMalloc(&t.dev, h.size() * sizeof(unsigned)));
-    CU(cudaMemcpy(t.dev, h.data(), h.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    OK(upload_table(t.dev, h.data(), h.size() * sizeof(unsigned)));
     G.pairs[w] = t;
     *out = t;
     return NAPA_OK;
@@ -653,6 +786,10 @@ NAPA_API int napafft_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(NAPA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
+    if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
+    if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
+    if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
+    G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;
     return NAPA_OK;
@@ -671,6 +808,9 @@ NAPA_API int napafft_shutdown(void) {
     G.pairs.clear();
     if (G.scratch) cudaFree(G.scratch);
     G.scratch = nullptr; G.scratch_bytes = 0;
+    for (auto &kv : G.counters) cudaFree(kv.second.first);
+    G.counters.clear();
+    if (G.h_error) { cudaFreeHost(G.h_error); G.h_error = nullptr; G.d_error = nullptr; }
     for (int i = 0; i < 2; i++) {
         if (G.dbuf[i]) cudaFree(G.dbuf[i]);
         if (G.pinned[i]) cudaFreeHost(G.pinned[i]);

@@ -162,6 +162,7 @@ struct PassParams {
     cplx *dst;
     long long src_batch_stride, dst_batch_stride;   // complex elements between batch items
     long long batch;                                // number of batch items in this launch
+    long long src_item_delta, dst_item_delta;       // added to the item index on either side (scratch ring)
     int tiles_per_item;                             // tiles inside one item (1 if PF_Q_IS_BATCH)
     int G;                                          // tile r -> (r / G, r % G)
     long long s_SA, s_SG, s_i, s_q;                 // src offset = (r/G)*SA + (r%G)*SG + pos(i)*s_i + q*s_q
@@ -180,6 +181,22 @@ struct PassParams {
 };
 
 __device__ __forceinline__ cplx ldg_c(const cplx *p) { return __ldg(p); }
+#ifdef NAPA_EMULATE
+template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p) { return *p; }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
+__device__ __forceinline__ void napa_nanosleep(unsigned) {}
+#else
+template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p) {
+    if (COHERENT) return __ldcg(p);
+    return *p;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void napa_nanosleep(unsigned ns) { __nanosleep(ns); }
+#endif
 // rev_w(x): reverse the low w bits of x (w = 0 -> 0)
 __device__ __forceinline__ int rev_bits(int x, int w) { return w ? (int)(__brev((unsigned)x) >> (32 - w)) : 0; }
 __device__ __forceinline__ long long rev_bits64(long long x, int w) {
@@ -248,19 +265,19 @@ __device__ __forceinline__ cplx big_twiddle(const PassParams &p, unsigned long l
     return cmul(hi, lo);
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(plan_threads(LOG2L), (plan_threads(LOG2L) <= 256 ? 2 : 1))
-fft_pass_kernel(const PassParams p) {
+// One tile of one digit pass.  `tile` counts tiles over the whole launch (item-major).  COHERENT
+// selects L2-only (ld.global.cg) data loads: required when the data was written earlier in the
+// SAME launch by another SM (persistent pipeline), where a stale L1 line would be a bug.
+template <int LOG2L, bool COHERENT>
+__device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm) {
     constexpr int L = 1 << LOG2L;
     constexpr int T = L / 16;
     constexpr int LOG2C = plan_log2c(LOG2L);
     constexpr int C = 1 << LOG2C;
-    NAPA_DYN_SMEM(cplx, sm);
 
     const int tid = threadIdx.x;
     const int q = tid & (C - 1);
     const int t = tid >> LOG2C;
-    const long long tile = blockIdx.x;
     const long long b = tile / p.tiles_per_item;
     const int r = (int)(tile - b * p.tiles_per_item);
     const int ra = r / p.G, rg = r - ra * p.G;
@@ -280,15 +297,15 @@ fft_pass_kernel(const PassParams p) {
 
     cplx v[16];
     if (valid) {
-        const cplx *src = p.src + item * p.src_batch_stride;
+        const cplx *src = p.src + (item + p.src_item_delta) * p.src_batch_stride;
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int i = t + m * T;
             const int pos = (flags & PF_IN_REV) ? rev_bits(i, LOG2L) : i;
             const long long off = s_xoff + (long long)pos * p.s_i;
-            cplx x = src[off];
+            cplx x = ld_data<COHERENT>(src + off);
             if (flags & PF_RIFFT_PRE) {
-                cplx y = src[off + p.aux_off];
+                cplx y = ld_data<COHERENT>(src + off + p.aux_off);
                 cplx w = ldg_c(p.r2tw + off);
                 x = cadd(cadd(x, y), cmul(csub(x, y), w));
             }
@@ -312,7 +329,7 @@ fft_pass_kernel(const PassParams p) {
     Stages<LOG2L, 0, 0>::run(v, sm, p.stage_tw, t, q);
 
     if (valid) {
-        cplx *dst = p.dst + item * p.dst_batch_stride;
+        cplx *dst = p.dst + (item + p.dst_item_delta) * p.dst_batch_stride;
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int k = t + m * T;
@@ -321,6 +338,116 @@ fft_pass_kernel(const PassParams p) {
             if (flags & PF_CONJ_OUT) y = cconj(y);
             const int pos = (flags & PF_OUT_REV) ? rev_bits(k, LOG2L) : k;
             dst[d_xoff + (long long)pos * p.d_i] = y;
+        }
+    }
+}
+
+template <int LOG2L>
+__global__ void __launch_bounds__(plan_threads(LOG2L), (plan_threads(LOG2L) <= 256 ? 2 : 1))
+fft_pass_kernel(const PassParams p) {
+    NAPA_DYN_SMEM(cplx, sm);
+    run_tile<LOG2L, false>(p, (long long)blockIdx.x, sm);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent two-pass pipeline: ONE launch runs both digit passes of every transform of a batch.
+// CTAs draw tickets from a global counter; tickets are ordered in phases
+//     phase ph:  pass A of chunk ph,  then pass B of chunk ph - LAG
+// so that by the time a pass-B tile of chunk c is drawn, the pass-A tiles of chunk c were drawn
+// >= LAG chunks earlier and their output is still L2-resident.  A pass-B tile waits (acquire
+// spin by one thread) until done[A][c] == tiles(c); deadlock-free because a waiter only ever
+// waits on lower tickets, which are held by running CTAs.  With a scratch ring (natural-order
+// output) pass A of chunk c additionally waits for pass B of chunk c - SLOTS to have drained
+// the slot it is about to overwrite.
+// ------------------------------------------------------------------------------------------
+struct PipeParams {
+    PassParams a, b;                 // pass A (first executed) and pass B
+    long long items;                 // batch
+    int chunk;                       // items per chunk
+    int nchunks;
+    int lag;                         // phases between pass A and pass B of a chunk
+    int slots;                       // scratch ring slots (0: intermediate lives in dst)
+    int a_dst_is_ring, b_src_is_ring;
+    long long tiles_per_item;        // same for both passes (C*L = 4096)
+    unsigned long long *ticket;      // zeroed before launch
+    unsigned *done;                  // [2][nchunks], zeroed before launch
+    int *error;                      // set to 1 if a wait timed out (never expected)
+};
+
+__device__ __forceinline__ long long pipe_tilesum(const PipeParams &p, long long k) {
+    // tiles of chunks [0, k)
+    long long items = k * p.chunk;
+    if (items > p.items) items = p.items;
+    return items * p.tiles_per_item;
+}
+__device__ __forceinline__ long long pipe_prefix(const PipeParams &p, long long ph) {
+    long long ka = ph < p.nchunks ? ph : p.nchunks;
+    long long kb = ph - p.lag;
+    kb = kb < 0 ? 0 : (kb < p.nchunks ? kb : p.nchunks);
+    return pipe_tilesum(p, ka) + pipe_tilesum(p, kb);
+}
+
+__device__ __forceinline__ void pipe_wait(const unsigned *ctr, unsigned target, int *error) {
+    unsigned spins = 0;
+    while (ld_acquire_u32(ctr) < target) {
+        napa_nanosleep(64);
+        if (++spins > (1u << 24)) { *error = 1; break; }      // ~seconds: bail out instead of hanging the GPU
+    }
+    __threadfence();
+}
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(256, 2) fft_pipeline_kernel(const PipeParams p) {
+    static_assert(plan_threads(LA) == 256 && plan_threads(LB) == 256, "pipeline passes use 256-thread tiles");
+    NAPA_DYN_SMEM(cplx, sm);
+    __shared__ long long s_ticket;
+    const long long nphase = (long long)p.nchunks + p.lag;
+    const long long total = pipe_prefix(p, nphase);
+    for (;;) {
+        __syncthreads();                       // previous tile is done with sm and s_ticket
+        if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(p.ticket, 1ull);
+        __syncthreads();
+        const long long tk = s_ticket;
+        if (tk >= total) break;
+        // phase = largest ph with prefix(ph) <= tk
+        long long lo = 0, hi = nphase;
+        while (hi - lo > 1) {
+            long long mid = (lo + hi) >> 1;
+            if (pipe_prefix(p, mid) <= tk) lo = mid; else hi = mid;
+        }
+        const long long ph = lo;
+        long long local = tk - pipe_prefix(p, ph);
+        const long long a_tiles = ph < p.nchunks ? pipe_tilesum(p, ph + 1) - pipe_tilesum(p, ph) : 0;
+        const bool is_a = local < a_tiles;
+        const long long c = is_a ? ph : ph - p.lag;
+        if (!is_a) local -= a_tiles;
+        const long long item0 = c * p.chunk;
+        const long long ctiles = pipe_tilesum(p, c + 1) - pipe_tilesum(p, c);
+        if (threadIdx.x == 0) {
+            if (is_a) {
+                if (p.slots && c >= p.slots) {
+                    const long long cc = c - p.slots;
+                    pipe_wait(p.done + p.nchunks + cc, (unsigned)(pipe_tilesum(p, cc + 1) - pipe_tilesum(p, cc)), p.error);
+                }
+            } else {
+                pipe_wait(p.done + c, (unsigned)ctiles, p.error);
+            }
+        }
+        __syncthreads();
+        const long long ring_delta = p.slots ? (long long)(c % p.slots) * p.chunk - item0 : 0;
+        if (is_a) {
+            PassParams pa = p.a;
+            if (p.a_dst_is_ring) pa.dst_item_delta = ring_delta;
+            run_tile<LA, true>(pa, item0 * p.tiles_per_item + local, sm);
+        } else {
+            PassParams pb = p.b;
+            if (p.b_src_is_ring) pb.src_item_delta = ring_delta;
+            run_tile<LB, true>(pb, item0 * p.tiles_per_item + local, sm);
+        }
+        __syncthreads();                       // all stores of this tile issued
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(p.done + (is_a ? 0 : p.nchunks) + c, 1u);
         }
     }
 }

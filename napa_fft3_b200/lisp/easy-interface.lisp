@@ -1,0 +1,101 @@
+;;; Keyword front-ends with the reference's signatures, defaults and aliasing rules
+;;; (easy-interface.lisp:3-95, interface.lisp:81-217).  Only the arithmetic moved to the GPU.
+(in-package "NAPA-FFT.B200")
+
+(defun power-of-two-p (x) (= 1 (logcount x)))               ; support.lisp:61-62
+
+(defun complex-samplify (vec &optional (size (length vec)))  ; support.lisp:64-93
+  (etypecase vec
+    (complex-sample-array vec)
+    (sequence (map-into (make-array size :element-type 'complex-sample)
+                        (lambda (x) (coerce x 'complex-sample)) vec))))
+(defun real-samplify (vec &optional (size (length vec)))     ; support.lisp:95-112
+  (etypecase vec
+    (real-sample-array vec)
+    (sequence (map-into (make-array size :element-type 'real-sample)
+                        (lambda (x) (coerce x 'real-sample)) vec))))
+
+(defun copy-or-replace (src dst)                              ; easy-interface.lisp:3-8
+  (cond ((eql src dst) dst) (dst (replace dst src)) (t (copy-seq src))))
+
+(defun fft (vec &key dst size (in-order t) (scale nil) (window nil))
+  (declare (type (or null complex-sample-array) dst))
+  (let* ((n (or size (length vec)))
+         (old vec)
+         (vec (complex-samplify vec n))
+         (dst (if (or (eql old vec) dst) (copy-or-replace vec dst) vec)))
+    (assert (power-of-two-p n))
+    (assert (>= (length vec) n))
+    (assert (>= (length dst) n))
+    (%c2c dst dst n 0 1 (scale-code scale) in-order window 0)))
+
+(defun ifft (vec &key dst size (in-order t) (scale t) (window nil))
+  (declare (type (or null complex-sample-array) dst))
+  (let* ((n (or size (length vec)))
+         (old vec)
+         (vec (complex-samplify vec n))
+         (dst (if (or (eql old vec) dst) (copy-or-replace vec dst) vec)))
+    (assert (power-of-two-p n))
+    (assert (>= (length vec) n))
+    (assert (>= (length dst) n))
+    (%c2c dst dst n 0 -1 (scale-code scale) in-order window 0)))
+
+(defun bit-reverse (vec &optional dst (size (length vec)))
+  (let ((elt (etypecase vec (complex-sample-array 0) (real-sample-array 1)))
+        (dst (copy-or-replace vec dst)))
+    (assert (>= (length vec) size))
+    (assert (>= (length dst) size))
+    (with-pinned-objects (dst)
+      (check (napafft-bit-reverse (vector-sap dst) (vector-sap dst) size 1 size elt)))
+    dst))
+
+;;; low-level generators: closures over the C ABI instead of run-time compiled Lisp
+(defun %ensure-twiddles (n forwardp)
+  (assert (power-of-two-p n))
+  (list :device-twiddles n forwardp))                        ; opaque: tables live on the device
+
+(defun %ensure-fft (direction scaling windowing n)
+  (check-type direction direction) (check-type scaling scaling) (check-type windowing windowing)
+  (assert (power-of-two-p n))
+  (let ((dir (direction-code direction)) (scale (scale-code scaling)))
+    (if windowing
+        (lambda (vec start window window-start twiddle)
+          (declare (ignore twiddle))
+          (%c2c vec vec n start dir scale nil window window-start))
+        (lambda (vec start twiddle)
+          (declare (ignore twiddle))
+          (%c2c vec vec n start dir scale nil nil 0)))))
+
+(defun %ensure-reverse (n &optional (eltype 'complex-sample))
+  (assert (member eltype '(complex-sample real-sample)))
+  (assert (power-of-two-p n))
+  (let ((elt (if (eq eltype 'complex-sample) 0 1))
+        (bytes (if (eq eltype 'complex-sample) 16 8)))
+    (lambda (vec start)
+      (with-pinned-objects (vec)
+        (let ((sap (sb-sys:sap+ (vector-sap vec) (* bytes start))))
+          (check (napafft-bit-reverse sap sap n 1 n elt))))
+      vec)))
+
+(defun get-reverse (n &optional (eltype 'complex-sample))
+  (let ((fun (%ensure-reverse n eltype)))
+    (lambda (vec) (funcall fun vec 0))))
+
+(defun get-fft (size &key (forward t) (scale (if forward nil :inv)) (in-order t))
+  (let ((dir (if forward 1 -1)) (scale (scale-code scale)))
+    (lambda (vec) (%c2c vec vec size 0 dir scale in-order nil 0))))
+
+(defun get-windowed-fft (size window-type &key (forward t) (scale (if forward nil :inv)) (in-order t))
+  (assert window-type)
+  (let ((dir (if forward 1 -1)) (scale (scale-code scale)))
+    (lambda (vec window) (%c2c vec vec size 0 dir scale in-order window 0))))
+
+;;; new export: B transforms of N samples stored back to back in one vector (H5 of SURVEY.md)
+(defun fft-batch (vec n batch &key (direction 1) (in-order t) (scale nil) (window nil) (dst vec))
+  (declare (type complex-sample-array vec dst))
+  (assert (>= (length vec) (* n batch)))
+  (with-pinned-objects (vec dst window)
+    (check (napafft-c2c (vector-sap vec) (vector-sap dst) n batch n (direction-code direction)
+                        (scale-code scale) (if in-order 1 0)
+                        (if window (vector-sap window) (int-sap 0)) (window-code window) 0)))
+  dst)
