@@ -257,17 +257,36 @@ struct Stages {
     }
 };
 
-// W_M^e from the two-level table
-__device__ __forceinline__ cplx big_twiddle(const PassParams &p, unsigned long long e) {
-    e &= p.tw_mask;
-    cplx lo = ldg_c(p.tw_lo + (e & ((1ull << p.tw_shift) - 1)));
-    cplx hi = ldg_c(p.tw_hi + (e >> p.tw_shift));
-    return cmul(hi, lo);
+// v[m] *= W_M^{(t + m*T) * col}, m < 16, from two table seeds and a depth-7 power tree:
+//   B = W^{t*col}, D = W^{T*col};  P_m = B * D^m  built from D^2, D^4, D^8.
+// 18 complex products instead of 32 dependent table look-ups; every seed load is issued at once.
+template <int T>
+__device__ __forceinline__ void apply_big_twiddle(cplx (&v)[16], const PassParams &p, int t, unsigned col) {
+    const unsigned long long eb = ((unsigned long long)t * col) & p.tw_mask;
+    const unsigned long long ed = ((unsigned long long)T * col) & p.tw_mask;
+    const unsigned long long lomask = (1ull << p.tw_shift) - 1;
+    const cplx blo = ldg_c(p.tw_lo + (eb & lomask)), bhi = ldg_c(p.tw_hi + (eb >> p.tw_shift));
+    const cplx dlo = ldg_c(p.tw_lo + (ed & lomask)), dhi = ldg_c(p.tw_hi + (ed >> p.tw_shift));
+    const cplx B = cmul(bhi, blo), D = cmul(dhi, dlo);
+    const cplx D2 = cmul(D, D), D4 = cmul(D2, D2), D8 = cmul(D4, D4);
+    cplx P[8];
+    P[0] = B; P[1] = cmul(B, D); P[2] = cmul(B, D2); P[3] = cmul(P[1], D2);
+    P[4] = cmul(B, D4); P[5] = cmul(P[1], D4); P[6] = cmul(P[2], D4); P[7] = cmul(P[3], D4);
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        v[m] = cmul(v[m], P[m]);
+        v[m + 8] = cmul(v[m + 8], cmul(P[m], D8));
+    }
 }
 
 // One tile of one digit pass.  `tile` counts tiles over the whole launch (item-major).  COHERENT
 // selects L2-only (ld.global.cg) data loads: required when the data was written earlier in the
 // SAME launch by another SM (persistent pipeline), where a stale L1 line would be a bug.
+//
+// Structure matters for memory-level parallelism: all 16 data loads of a thread are issued
+// back to back into v[], and every optional fusion is a separate warp-uniform branch over the
+// whole register array (not a predicated snippet per element), so that unused fusions cost
+// nothing and used ones do not serialise the loads.
 template <int LOG2L, bool COHERENT>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm) {
     constexpr int L = 1 << LOG2L;
@@ -297,30 +316,62 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 
     cplx v[16];
     if (valid) {
-        const cplx *src = p.src + (item + p.src_item_delta) * p.src_batch_stride;
+        const cplx *src = p.src + (item + p.src_item_delta) * p.src_batch_stride + s_xoff;
+        const long long s_i = p.s_i;
+        if (flags & PF_IN_REV) {
 #pragma unroll
-        for (int m = 0; m < 16; m++) {
-            const int i = t + m * T;
-            const int pos = (flags & PF_IN_REV) ? rev_bits(i, LOG2L) : i;
-            const long long off = s_xoff + (long long)pos * p.s_i;
-            cplx x = ld_data<COHERENT>(src + off);
-            if (flags & PF_RIFFT_PRE) {
-                cplx y = ld_data<COHERENT>(src + off + p.aux_off);
-                cplx w = ldg_c(p.r2tw + off);
-                x = cadd(cadd(x, y), cmul(csub(x, y), w));
-            }
-            if (flags & PF_SCALE) x = cscale(x, p.scale);
-            if (flags & (PF_WIN_REAL | PF_WIN_CPLX)) {
-                long long widx = off;
-                if (flags & PF_WIN_REV) widx = rev_bits64(off, p.lgN);
-                widx += item * p.window_batch_stride;
-                if (flags & PF_WIN_REAL) x = cscale(x, __ldg(reinterpret_cast<const double *>(p.window) + widx));
-                else x = cmul(x, ldg_c(reinterpret_cast<const cplx *>(p.window) + widx));
-            }
-            if (flags & PF_CONJ_IN) x = cconj(x);
-            if (flags & PF_TW_LOAD) x = cmul(x, big_twiddle(p, (unsigned long long)i * col));
-            v[m] = x;
+            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)(t + m * T) * s_i);
         }
+        if (flags & PF_RIFFT_PRE) {
+            // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177)
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + m * T, LOG2L) : t + m * T) * s_i;
+                const cplx y = ld_data<COHERENT>(src - s_xoff + off + p.aux_off);
+                const cplx w = ldg_c(p.r2tw + off);
+                v[m] = cadd(cadd(v[m], y), cmul(csub(v[m], y), w));
+            }
+        }
+        if (flags & PF_SCALE) {
+            const double sc = p.scale;
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = cscale(v[m], sc);
+        }
+        if (flags & (PF_WIN_REAL | PF_WIN_CPLX)) {
+            const long long wbase = item * p.window_batch_stride;
+            long long widx[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + m * T, LOG2L) : t + m * T) * s_i;
+                widx[m] = wbase + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off);
+            }
+            if (flags & PF_WIN_REAL) {
+                const double *w = reinterpret_cast<const double *>(p.window);
+                double wv[16];
+#pragma unroll
+                for (int m = 0; m < 16; m++) wv[m] = __ldg(w + widx[m]);
+#pragma unroll
+                for (int m = 0; m < 16; m++) v[m] = cscale(v[m], wv[m]);
+            } else {
+                const cplx *w = reinterpret_cast<const cplx *>(p.window);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    cplx wv[8];
+#pragma unroll
+                    for (int m = 0; m < 8; m++) wv[m] = ldg_c(w + widx[8 * h + m]);
+#pragma unroll
+                    for (int m = 0; m < 8; m++) v[8 * h + m] = cmul(v[8 * h + m], wv[m]);
+                }
+            }
+        }
+        if (flags & PF_CONJ_IN) {
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
+        }
+        if (flags & PF_TW_LOAD) apply_big_twiddle<T>(v, p, t, col);
     } else {
 #pragma unroll
         for (int m = 0; m < 16; m++) v[m] = make_double2(0.0, 0.0);
@@ -329,15 +380,19 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     Stages<LOG2L, 0, 0>::run(v, sm, p.stage_tw, t, q);
 
     if (valid) {
-        cplx *dst = p.dst + (item + p.dst_item_delta) * p.dst_batch_stride;
+        if (flags & PF_TW_STORE) apply_big_twiddle<T>(v, p, t, col);
+        if (flags & PF_CONJ_OUT) {
 #pragma unroll
-        for (int m = 0; m < 16; m++) {
-            const int k = t + m * T;
-            cplx y = v[m];
-            if (flags & PF_TW_STORE) y = cmul(y, big_twiddle(p, (unsigned long long)k * col));
-            if (flags & PF_CONJ_OUT) y = cconj(y);
-            const int pos = (flags & PF_OUT_REV) ? rev_bits(k, LOG2L) : k;
-            dst[d_xoff + (long long)pos * p.d_i] = y;
+            for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
+        }
+        cplx *dst = p.dst + (item + p.dst_item_delta) * p.dst_batch_stride + d_xoff;
+        const long long d_i = p.d_i;
+        if (flags & PF_OUT_REV) {
+#pragma unroll
+            for (int m = 0; m < 16; m++) dst[(long long)rev_bits(t + m * T, LOG2L) * d_i] = v[m];
+        } else {
+#pragma unroll
+            for (int m = 0; m < 16; m++) dst[(long long)(t + m * T) * d_i] = v[m];
         }
     }
 }
