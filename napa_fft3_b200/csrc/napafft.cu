@@ -436,6 +436,8 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             p2.flags = inv ? napa::PF_CONJ_OUT : 0;
             p2.d_SA = 1LL << napa::plan_log2c(d[1]); p2.d_SG = 0; p2.d_i = 1LL << d[0]; p2.d_q = 1;
             pp.a_dst_is_ring = 1; pp.b_src_is_ring = 1;
+            p1.src_hint = napa::HINT_STREAM; p1.dst_hint = napa::HINT_KEEP;
+            p2.src_hint = napa::HINT_KEEP; p2.dst_hint = napa::HINT_STREAM;
             OK(launch_pipeline(d[0], d[1], pp, st));
         } else {
             // bit-reversed layouts: in place on dst after the first pass, no scratch
@@ -459,6 +461,9 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                 if (inv && step == 0) q.flags |= napa::PF_CONJ_IN;
                 if (inv && step == 1) q.flags |= napa::PF_CONJ_OUT;
                 if (step == 0) first_pass_fusions(q, o, n, false);
+                // in place: the intermediate lives in dst between the passes
+                q.src_hint = step == 0 ? napa::HINT_STREAM : napa::HINT_KEEP;
+                q.dst_hint = step == 0 ? napa::HINT_KEEP : napa::HINT_STREAM;
             }
             OK(launch_pipeline(d[order[0]], d[order[1]], pp, st));
         }

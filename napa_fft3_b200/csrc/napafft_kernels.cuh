@@ -162,7 +162,7 @@ struct PassParams {
     cplx *dst;
     long long src_batch_stride, dst_batch_stride;   // complex elements between batch items
     long long batch;                                // number of batch items in this launch
-    long long src_item_delta, dst_item_delta;       // added to the item index on either side (scratch ring)
+    int src_hint, dst_hint;                         // HINT_* L2 eviction hints of the data path
     int tiles_per_item;                             // tiles inside one item (1 if PF_Q_IS_BATCH)
     int G;                                          // tile r -> (r / G, r % G)
     long long s_SA, s_SG, s_i, s_q;                 // src offset = (r/G)*SA + (r%G)*SG + pos(i)*s_i + q*s_q
@@ -181,14 +181,43 @@ struct PassParams {
 };
 
 __device__ __forceinline__ cplx ldg_c(const cplx *p) { return __ldg(p); }
+// Data-path loads/stores carry an L2 eviction hint (HINT_*): streaming operands (user src / dst,
+// touched once) are evict-first, the L2-resident intermediate of the two-pass pipeline is
+// evict-last, so that the stream does not push the intermediate out to HBM.
+enum { HINT_NORMAL = 0, HINT_STREAM = 1, HINT_KEEP = 2 };
 #ifdef NAPA_EMULATE
-template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p) { return *p; }
+struct L2Policies { int dummy; };
+__device__ __forceinline__ L2Policies make_policies() { return L2Policies{0}; }
+template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, int, const L2Policies &) { return *p; }
+__device__ __forceinline__ void st_data(cplx *p, cplx v, int, const L2Policies &) { *p = v; }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
 __device__ __forceinline__ void napa_nanosleep(unsigned) {}
 #else
-template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p) {
-    if (COHERENT) return __ldcg(p);
-    return *p;
+struct L2Policies { unsigned long long first, last; };
+__device__ __forceinline__ L2Policies make_policies() {
+    L2Policies pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol.first));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol.last));
+    return pol;
+}
+// COHERENT: L2-only (.cg) because another SM may have written the line earlier in this launch
+template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, int hint, const L2Policies &pol) {
+    cplx v;
+    if (hint == HINT_NORMAL) {
+        if (COHERENT) return __ldcg(p);
+        return *p;
+    }
+    const unsigned long long policy = hint == HINT_STREAM ? pol.first : pol.last;
+    if (COHERENT)
+        asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy) : "memory");
+    else
+        asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_data(cplx *p, cplx v, int hint, const L2Policies &pol) {
+    if (hint == HINT_NORMAL) { *p = v; return; }
+    const unsigned long long policy = hint == HINT_STREAM ? pol.first : pol.last;
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
@@ -288,7 +317,10 @@ __device__ __forceinline__ void apply_big_twiddle(cplx (&v)[16], const PassParam
 // whole register array (not a predicated snippet per element), so that unused fusions cost
 // nothing and used ones do not serialise the loads.
 template <int LOG2L, bool COHERENT>
-__device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm) {
+__device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
+                                         const long long src_item_delta, const long long dst_item_delta) {
+    const L2Policies pol = make_policies();
+    const int src_hint = p.src_hint, dst_hint = p.dst_hint;
     constexpr int L = 1 << LOG2L;
     constexpr int T = L / 16;
     constexpr int LOG2C = plan_log2c(LOG2L);
@@ -316,21 +348,21 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 
     cplx v[16];
     if (valid) {
-        const cplx *src = p.src + (item + p.src_item_delta) * p.src_batch_stride + s_xoff;
+        const cplx *src = p.src + (item + src_item_delta) * p.src_batch_stride + s_xoff;
         const long long s_i = p.s_i;
         if (flags & PF_IN_REV) {
 #pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i);
+            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i, src_hint, pol);
         } else {
 #pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)(t + m * T) * s_i);
+            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)(t + m * T) * s_i, src_hint, pol);
         }
         if (flags & PF_RIFFT_PRE) {
             // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177)
 #pragma unroll
             for (int m = 0; m < 16; m++) {
                 const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + m * T, LOG2L) : t + m * T) * s_i;
-                const cplx y = ld_data<COHERENT>(src - s_xoff + off + p.aux_off);
+                const cplx y = ld_data<COHERENT>(src - s_xoff + off + p.aux_off, src_hint, pol);
                 const cplx w = ldg_c(p.r2tw + off);
                 v[m] = cadd(cadd(v[m], y), cmul(csub(v[m], y), w));
             }
@@ -385,14 +417,14 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
         }
-        cplx *dst = p.dst + (item + p.dst_item_delta) * p.dst_batch_stride + d_xoff;
+        cplx *dst = p.dst + (item + dst_item_delta) * p.dst_batch_stride + d_xoff;
         const long long d_i = p.d_i;
         if (flags & PF_OUT_REV) {
 #pragma unroll
-            for (int m = 0; m < 16; m++) dst[(long long)rev_bits(t + m * T, LOG2L) * d_i] = v[m];
+            for (int m = 0; m < 16; m++) st_data(dst + (long long)rev_bits(t + m * T, LOG2L) * d_i, v[m], dst_hint, pol);
         } else {
 #pragma unroll
-            for (int m = 0; m < 16; m++) dst[(long long)(t + m * T) * d_i] = v[m];
+            for (int m = 0; m < 16; m++) st_data(dst + (long long)(t + m * T) * d_i, v[m], dst_hint, pol);
         }
     }
 }
@@ -401,7 +433,7 @@ template <int LOG2L>
 __global__ void __launch_bounds__(plan_threads(LOG2L), (plan_threads(LOG2L) <= 256 ? 2 : 1))
 fft_pass_kernel(const PassParams p) {
     NAPA_DYN_SMEM(cplx, sm);
-    run_tile<LOG2L, false>(p, (long long)blockIdx.x, sm);
+    run_tile<LOG2L, false>(p, (long long)blockIdx.x, sm, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -455,51 +487,56 @@ template <int LA, int LB>
 __global__ void __launch_bounds__(256, 2) fft_pipeline_kernel(const PipeParams p) {
     static_assert(plan_threads(LA) == 256 && plan_threads(LB) == 256, "pipeline passes use 256-thread tiles");
     NAPA_DYN_SMEM(cplx, sm);
-    __shared__ long long s_ticket;
+    __shared__ long long s_tile;       // global tile index of the decoded ticket, -1 = no more work
+    __shared__ long long s_delta;      // scratch-ring item delta
+    __shared__ int s_chunk, s_is_a;
     const long long nphase = (long long)p.nchunks + p.lag;
     const long long total = pipe_prefix(p, nphase);
+    long long next_ticket = 0;
+    if (threadIdx.x == 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
     for (;;) {
-        __syncthreads();                       // previous tile is done with sm and s_ticket
-        if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(p.ticket, 1ull);
-        __syncthreads();
-        const long long tk = s_ticket;
-        if (tk >= total) break;
-        // phase = largest ph with prefix(ph) <= tk
-        long long lo = 0, hi = nphase;
-        while (hi - lo > 1) {
-            long long mid = (lo + hi) >> 1;
-            if (pipe_prefix(p, mid) <= tk) lo = mid; else hi = mid;
-        }
-        const long long ph = lo;
-        long long local = tk - pipe_prefix(p, ph);
-        const long long a_tiles = ph < p.nchunks ? pipe_tilesum(p, ph + 1) - pipe_tilesum(p, ph) : 0;
-        const bool is_a = local < a_tiles;
-        const long long c = is_a ? ph : ph - p.lag;
-        if (!is_a) local -= a_tiles;
-        const long long item0 = c * p.chunk;
-        const long long ctiles = pipe_tilesum(p, c + 1) - pipe_tilesum(p, c);
         if (threadIdx.x == 0) {
-            if (is_a) {
-                if (p.slots && c >= p.slots) {
-                    const long long cc = c - p.slots;
-                    pipe_wait(p.done + p.nchunks + cc, (unsigned)(pipe_tilesum(p, cc + 1) - pipe_tilesum(p, cc)), p.error);
-                }
+            // one thread decodes the ticket, waits for its dependencies and prefetches the next ticket
+            const long long tk = next_ticket;
+            if (tk >= total) {
+                s_tile = -1;
             } else {
-                pipe_wait(p.done + c, (unsigned)ctiles, p.error);
+                next_ticket = (long long)atomicAdd(p.ticket, 1ull);    // latency hidden behind this tile
+                long long lo = 0, hi = nphase;                         // phase = largest ph with prefix(ph) <= tk
+                while (hi - lo > 1) {
+                    const long long mid = (lo + hi) >> 1;
+                    if (pipe_prefix(p, mid) <= tk) lo = mid; else hi = mid;
+                }
+                const long long ph = lo;
+                long long local = tk - pipe_prefix(p, ph);
+                const long long a_tiles = ph < p.nchunks ? pipe_tilesum(p, ph + 1) - pipe_tilesum(p, ph) : 0;
+                const bool is_a = local < a_tiles;
+                const long long c = is_a ? ph : ph - p.lag;
+                if (!is_a) local -= a_tiles;
+                const long long item0 = c * p.chunk;
+                if (is_a) {
+                    if (p.slots && c >= p.slots) {
+                        const long long cc = c - p.slots;
+                        pipe_wait(p.done + p.nchunks + cc, (unsigned)(pipe_tilesum(p, cc + 1) - pipe_tilesum(p, cc)), p.error);
+                    }
+                } else {
+                    pipe_wait(p.done + c, (unsigned)(pipe_tilesum(p, c + 1) - pipe_tilesum(p, c)), p.error);
+                }
+                s_tile = item0 * p.tiles_per_item + local;
+                s_delta = p.slots ? (long long)(c % p.slots) * p.chunk - item0 : 0;
+                s_chunk = (int)c;
+                s_is_a = is_a ? 1 : 0;
             }
         }
-        __syncthreads();
-        const long long ring_delta = p.slots ? (long long)(c % p.slots) * p.chunk - item0 : 0;
-        if (is_a) {
-            PassParams pa = p.a;
-            if (p.a_dst_is_ring) pa.dst_item_delta = ring_delta;
-            run_tile<LA, true>(pa, item0 * p.tiles_per_item + local, sm);
-        } else {
-            PassParams pb = p.b;
-            if (p.b_src_is_ring) pb.src_item_delta = ring_delta;
-            run_tile<LB, true>(pb, item0 * p.tiles_per_item + local, sm);
-        }
-        __syncthreads();                       // all stores of this tile issued
+        __syncthreads();                       // publishes the ticket; previous tile is done with sm
+        const long long tile = s_tile;
+        if (tile < 0) break;
+        const long long delta = s_delta;
+        const int c = s_chunk;
+        const bool is_a = s_is_a != 0;
+        if (is_a) run_tile<LA, true>(p.a, tile, sm, 0, p.a_dst_is_ring ? delta : 0);
+        else run_tile<LB, true>(p.b, tile, sm, p.b_src_is_ring ? delta : 0, 0);
+        __syncthreads();                       // all stores of this tile issued; s_* may be rewritten
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(p.done + (is_a ? 0 : p.nchunks) + c, 1u);
