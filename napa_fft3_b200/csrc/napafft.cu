@@ -77,6 +77,7 @@ struct State {
     size_t pipe_chunk_bytes = 8u << 20;   // chunk of the persistent pipeline
     int pipe_lag = 3;                     // phases between the two passes of a chunk
     bool use_pipeline = true;
+    bool use_persist = true;
     bool attrs_set = false;
     int num_sms = 148;
     std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream ticket/done block
@@ -193,7 +194,7 @@ static int ensure_scratch(size_t bytes) {
 // ------------------------------------------------------------------------------------------
 // kernel launch table
 // ------------------------------------------------------------------------------------------
-typedef void (*pass_fn)(const PassParams);
+typedef void (*pass_fn)(const PassParams, const long long, const int);
 static pass_fn pass_kernel(int l) {
     switch (l) {
     case 4: return napa::fft_pass_kernel<4>;
@@ -227,7 +228,11 @@ static int launch_pass(int l, PassParams &p, long long ntiles, cudaStream_t st) 
     if (ntiles <= 0) return NAPA_OK;
     if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
     pass_fn fn = pass_kernel(l);
-    NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p);
+    // big launches of exchange-bearing sizes run persistent CTAs with cp.async prefetch
+    const long long resident = (long long)G.num_sms * (napa::plan_threads(l) <= 256 ? 2 : 1);
+    const int persist = G.use_persist && napa::plan_nstages(l) > 1 && ntiles >= 4 * resident ? 1 : 0;
+    const long long grid = persist ? resident : ntiles;
+    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p, ntiles, persist);
     g_launches++;
     return NAPA_OK;
 }
@@ -794,6 +799,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
     if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
+    if (const char *env = getenv("NAPAFFT_NO_PERSIST")) G.use_persist = atoi(env) == 0;
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;

@@ -192,6 +192,9 @@ template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, 
 __device__ __forceinline__ void st_data(cplx *p, cplx v, int, const L2Policies &) { *p = v; }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
 __device__ __forceinline__ void napa_nanosleep(unsigned) {}
+__device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int, const L2Policies &) { *s = *g; }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
 #else
 struct L2Policies { unsigned long long first, last; };
 __device__ __forceinline__ L2Policies make_policies() {
@@ -225,6 +228,18 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ void napa_nanosleep(unsigned ns) { __nanosleep(ns); }
+// 16-byte asynchronous global->shared copy, L2-only (.cg) hence coherent with other SMs' writes
+__device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int hint, const L2Policies &pol) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+    if (hint == HINT_NORMAL) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
+    } else {
+        const unsigned long long policy = hint == HINT_STREAM ? pol.first : pol.last;
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(sa), "l"(g), "l"(policy) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #endif
 // rev_w(x): reverse the low w bits of x (w = 0 -> 0)
 __device__ __forceinline__ int rev_bits(int x, int w) { return w ? (int)(__brev((unsigned)x) >> (32 - w)) : 0; }
@@ -232,25 +247,33 @@ __device__ __forceinline__ long long rev_bits64(long long x, int w) {
     return w ? (long long)(__brevll((unsigned long long)x) >> (64 - w)) : 0;
 }
 
-template <int LOG2L, int STAGE, int LOG2NS>
+// shared-memory slot of (position, interleaved transform q); see tools/bank_check.py
+template <int LOG2L>
+__device__ __forceinline__ int smem_phys(int pos, int q) {
+    return ((pos + (pos >> plan_padshift(LOG2L))) << plan_log2c(LOG2L)) + q;
+}
+
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// PRESYNC0: the tile's input was staged in sm (thread-private slots); everyone must have read its
+// staged input before stage 0 scatters.  `hook` runs right after the gather of the LAST stage, i.e.
+// at the first moment sm is free again (used to issue the next tile's cp.async prefetch).
+template <int LOG2L, int STAGE, int LOG2NS, bool PRESYNC0, class Hook>
 struct Stages {
     static constexpr int L = 1 << LOG2L;
     static constexpr int T = L / 16;
-    static constexpr int LOG2C = plan_log2c(LOG2L);
-    static constexpr int PADSH = plan_padshift(LOG2L);
     static constexpr int NSTAGES = plan_nstages(LOG2L);
     static constexpr int LOG2R = plan_log2radix(LOG2L, STAGE);
     static constexpr int R = 1 << LOG2R;
     static constexpr int NB = 16 / R;
     static constexpr int NS = 1 << LOG2NS;
 
-    static __device__ __forceinline__ int phys(int pos, int q) { return ((pos + (pos >> PADSH)) << LOG2C) + q; }
-
-    static __device__ __forceinline__ void run(cplx (&v)[16], cplx *sm, const cplx *__restrict__ tw, int t, int q) {
+    static __device__ __forceinline__ void run(cplx (&v)[16], cplx *sm, const cplx *__restrict__ tw, int t, int q, Hook &hook) {
         if constexpr (STAGE > 0) {
             // exchange: previous stage wrote its scattered outputs; gather t + m*T
 #pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = sm[phys(t + m * T, q)];
+            for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L>(t + m * T, q)];
+            if constexpr (STAGE + 1 == NSTAGES) hook();
             // twiddle W_{NS*R}^{(jb % NS) * s} on input s of butterfly jb = t + u*T
 #pragma unroll
             for (int u = 0; u < NB; u++) {
@@ -272,16 +295,16 @@ struct Stages {
             for (int s = 0; s < R; s++) v[u + s * NB] = w[s];
         }
         if constexpr (STAGE + 1 < NSTAGES) {
-            if constexpr (STAGE > 0) __syncthreads();   // everyone has gathered before we overwrite
+            if constexpr (STAGE > 0 || PRESYNC0) __syncthreads();   // everyone has gathered before we overwrite
 #pragma unroll
             for (int u = 0; u < NB; u++) {
                 int jb = t + u * T;
                 int base = ((jb >> LOG2NS) << (LOG2NS + LOG2R)) + (jb & (NS - 1));
 #pragma unroll
-                for (int s = 0; s < R; s++) sm[phys(base + s * NS, q)] = v[u + s * NB];
+                for (int s = 0; s < R; s++) sm[smem_phys<LOG2L>(base + s * NS, q)] = v[u + s * NB];
             }
             __syncthreads();
-            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R>::run(v, sm, tw, t, q);
+            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PRESYNC0, Hook>::run(v, sm, tw, t, q, hook);
         }
     }
 };
@@ -308,49 +331,94 @@ __device__ __forceinline__ void apply_big_twiddle(cplx (&v)[16], const PassParam
     }
 }
 
-// One tile of one digit pass.  `tile` counts tiles over the whole launch (item-major).  COHERENT
-// selects L2-only (ld.global.cg) data loads: required when the data was written earlier in the
-// SAME launch by another SM (persistent pipeline), where a stale L1 line would be a bug.
+// Where a thread's 16 points of a tile live.  `tile` counts tiles over the whole launch (item-major).
+struct TileCtx {
+    int q, t;
+    long long item;
+    bool valid;
+    long long s_xoff, d_xoff;
+    unsigned col;                    // column offset inside the [L][B] sub-matrix (twiddle exponent)
+};
+template <int LOG2L>
+__device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long tile) {
+    constexpr int LOG2C = plan_log2c(LOG2L);
+    constexpr int C = 1 << LOG2C;
+    TileCtx c;
+    const int tid = threadIdx.x;
+    c.q = tid & (C - 1);
+    c.t = tid >> LOG2C;
+    const long long b = tile / p.tiles_per_item;
+    const int r = (int)(tile - b * p.tiles_per_item);
+    const int ra = r / p.G, rg = r - ra * p.G;
+    c.item = b;
+    c.s_xoff = (long long)ra * p.s_SA + (long long)rg * p.s_SG;
+    c.d_xoff = (long long)ra * p.d_SA + (long long)rg * p.d_SG;
+    if (p.flags & PF_Q_IS_BATCH) {
+        c.item = b * C + c.q;
+    } else {
+        c.s_xoff += c.q * p.s_q;
+        c.d_xoff += c.q * p.d_q;
+    }
+    c.valid = c.item < p.batch;
+    c.col = (unsigned)(rg * C + c.q);
+    return c;
+}
+
+// Asynchronously copy this thread's 16 input points of `tile` into its own shared-memory slots
+// (cp.async.cg: L2-coherent, no register staging).  The same thread gathers them later, so the
+// only synchronisation needed is cp.async.wait_group by that thread.
+template <int LOG2L>
+__device__ __forceinline__ void tile_prefetch(const PassParams &p, const long long tile, cplx *sm, const long long src_item_delta) {
+    constexpr int T = (1 << LOG2L) / 16;
+    const L2Policies pol = make_policies();
+    const TileCtx c = tile_ctx<LOG2L>(p, tile);
+    if (c.valid) {
+        const cplx *src = p.src + (c.item + src_item_delta) * p.src_batch_stride + c.s_xoff;
+        const long long s_i = p.s_i;
+        const int hint = p.src_hint;
+        if (p.flags & PF_IN_REV) {
+#pragma unroll
+            for (int m = 0; m < 16; m++)
+                cp_async16(sm + smem_phys<LOG2L>(c.t + m * T, c.q), src + (long long)rev_bits(c.t + m * T, LOG2L) * s_i, hint, pol);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 16; m++)
+                cp_async16(sm + smem_phys<LOG2L>(c.t + m * T, c.q), src + (long long)(c.t + m * T) * s_i, hint, pol);
+        }
+    }
+    cp_async_commit();
+}
+
+// One tile of one digit pass.  COHERENT selects L2-only (ld.global.cg) data loads: required when
+// the data was written earlier in the SAME launch by another SM (persistent pipeline), where a
+// stale L1 line would be a bug.  STAGED: the input was prefetched into sm by tile_prefetch.
 //
 // Structure matters for memory-level parallelism: all 16 data loads of a thread are issued
 // back to back into v[], and every optional fusion is a separate warp-uniform branch over the
 // whole register array (not a predicated snippet per element), so that unused fusions cost
 // nothing and used ones do not serialise the loads.
-template <int LOG2L, bool COHERENT>
+template <int LOG2L, bool COHERENT, bool STAGED, class Hook>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
-                                         const long long src_item_delta, const long long dst_item_delta) {
-    const L2Policies pol = make_policies();
-    const int src_hint = p.src_hint, dst_hint = p.dst_hint;
+                                         const long long src_item_delta, const long long dst_item_delta, Hook &hook) {
     constexpr int L = 1 << LOG2L;
     constexpr int T = L / 16;
-    constexpr int LOG2C = plan_log2c(LOG2L);
-    constexpr int C = 1 << LOG2C;
-
-    const int tid = threadIdx.x;
-    const int q = tid & (C - 1);
-    const int t = tid >> LOG2C;
-    const long long b = tile / p.tiles_per_item;
-    const int r = (int)(tile - b * p.tiles_per_item);
-    const int ra = r / p.G, rg = r - ra * p.G;
+    static_assert(!STAGED || plan_nstages(LOG2L) > 1, "staging needs a shared-memory buffer");
+    const L2Policies pol = make_policies();
+    const int src_hint = p.src_hint, dst_hint = p.dst_hint;
+    const TileCtx c = tile_ctx<LOG2L>(p, tile);
+    const int t = c.t, q = c.q;
     const unsigned flags = p.flags;
-
-    long long item = b;
-    long long s_xoff = (long long)ra * p.s_SA + (long long)rg * p.s_SG;
-    long long d_xoff = (long long)ra * p.d_SA + (long long)rg * p.d_SG;
-    if (flags & PF_Q_IS_BATCH) {
-        item = b * C + q;
-    } else {
-        s_xoff += q * p.s_q;
-        d_xoff += q * p.d_q;
-    }
-    const bool valid = item < p.batch;
-    const unsigned col = (unsigned)(rg * C + q);       // column offset inside the [L][B] sub-matrix
+    const long long s_xoff = c.s_xoff;
 
     cplx v[16];
-    if (valid) {
-        const cplx *src = p.src + (item + src_item_delta) * p.src_batch_stride + s_xoff;
+    if (STAGED) cp_async_wait_all();
+    if (c.valid) {
+        const cplx *src = p.src + (c.item + src_item_delta) * p.src_batch_stride + s_xoff;
         const long long s_i = p.s_i;
-        if (flags & PF_IN_REV) {
+        if (STAGED) {
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L>(t + m * T, q)];
+        } else if (flags & PF_IN_REV) {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i, src_hint, pol);
         } else {
@@ -373,7 +441,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             for (int m = 0; m < 16; m++) v[m] = cscale(v[m], sc);
         }
         if (flags & (PF_WIN_REAL | PF_WIN_CPLX)) {
-            const long long wbase = item * p.window_batch_stride;
+            const long long wbase = c.item * p.window_batch_stride;
             long long widx[16];
 #pragma unroll
             for (int m = 0; m < 16; m++) {
@@ -403,21 +471,21 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
         }
-        if (flags & PF_TW_LOAD) apply_big_twiddle<T>(v, p, t, col);
+        if (flags & PF_TW_LOAD) apply_big_twiddle<T>(v, p, t, c.col);
     } else {
 #pragma unroll
         for (int m = 0; m < 16; m++) v[m] = make_double2(0.0, 0.0);
     }
 
-    Stages<LOG2L, 0, 0>::run(v, sm, p.stage_tw, t, q);
+    Stages<LOG2L, 0, 0, STAGED, Hook>::run(v, sm, p.stage_tw, t, q, hook);
 
-    if (valid) {
-        if (flags & PF_TW_STORE) apply_big_twiddle<T>(v, p, t, col);
+    if (c.valid) {
+        if (flags & PF_TW_STORE) apply_big_twiddle<T>(v, p, t, c.col);
         if (flags & PF_CONJ_OUT) {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
         }
-        cplx *dst = p.dst + (item + dst_item_delta) * p.dst_batch_stride + d_xoff;
+        cplx *dst = p.dst + (c.item + dst_item_delta) * p.dst_batch_stride + c.d_xoff;
         const long long d_i = p.d_i;
         if (flags & PF_OUT_REV) {
 #pragma unroll
@@ -429,11 +497,33 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     }
 }
 
+// Single-pass transforms (n <= 2^13).  Small launches: one tile per CTA, loads straight to
+// registers.  Large launches (persist != 0): persistent CTAs walk tiles blockIdx.x, +gridDim.x, ...
+// and prefetch the next tile with cp.async while the last radix stage of the current one runs.
 template <int LOG2L>
 __global__ void __launch_bounds__(plan_threads(LOG2L), (plan_threads(LOG2L) <= 256 ? 2 : 1))
-fft_pass_kernel(const PassParams p) {
+fft_pass_kernel(const PassParams p, const long long ntiles, const int persist) {
     NAPA_DYN_SMEM(cplx, sm);
-    run_tile<LOG2L, false>(p, (long long)blockIdx.x, sm, 0, 0);
+    if constexpr (plan_nstages(LOG2L) > 1) {
+        if (persist) {
+            long long tile = blockIdx.x;
+            if (tile >= ntiles) return;
+            tile_prefetch<LOG2L>(p, tile, sm, 0);
+            for (;;) {
+                const long long next = tile + gridDim.x;
+                auto hook = [&]() {
+                    __syncthreads();                       // sm is free: everyone gathered the last exchange
+                    if (next < ntiles) tile_prefetch<LOG2L>(p, next, sm, 0);
+                };
+                run_tile<LOG2L, false, true>(p, tile, sm, 0, 0, hook);
+                if (next >= ntiles) break;
+                tile = next;
+            }
+            return;
+        }
+    }
+    NoHook nh;
+    run_tile<LOG2L, false, false>(p, (long long)blockIdx.x, sm, 0, 0, nh);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -446,6 +536,8 @@ fft_pass_kernel(const PassParams p) {
 // waits on lower tickets, which are held by running CTAs.  With a scratch ring (natural-order
 // output) pass A of chunk c additionally waits for pass B of chunk c - SLOTS to have drained
 // the slot it is about to overwrite.
+// The loop is software-pipelined: while the last radix stage of tile k runs, the input of tile
+// k+1 (already ticketed, dependencies checked without blocking) is in flight via cp.async.
 // ------------------------------------------------------------------------------------------
 struct PipeParams {
     PassParams a, b;                 // pass A (first executed) and pass B
@@ -474,9 +566,52 @@ __device__ __forceinline__ long long pipe_prefix(const PipeParams &p, long long 
     return pipe_tilesum(p, ka) + pipe_tilesum(p, kb);
 }
 
-__device__ __forceinline__ void pipe_wait(const unsigned *ctr, unsigned target, int *error) {
+struct PipeWork {                    // a decoded ticket
+    long long tile;                  // global tile index, -1 = no more work
+    long long delta;                 // scratch-ring item delta
+    int chunk, is_a;
+    int ready;                       // dependencies satisfied (checked without blocking)
+    const unsigned *dep; unsigned dep_target;
+};
+
+__device__ __forceinline__ PipeWork pipe_decode(const PipeParams &p, const long long tk, const long long nphase, const long long total) {
+    PipeWork w;
+    w.tile = -1; w.delta = 0; w.chunk = 0; w.is_a = 0; w.ready = 1; w.dep = nullptr; w.dep_target = 0;
+    if (tk >= total) return w;
+    long long lo = 0, hi = nphase;                         // phase = largest ph with prefix(ph) <= tk
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (pipe_prefix(p, mid) <= tk) lo = mid; else hi = mid;
+    }
+    const long long ph = lo;
+    long long local = tk - pipe_prefix(p, ph);
+    const long long a_tiles = ph < p.nchunks ? pipe_tilesum(p, ph + 1) - pipe_tilesum(p, ph) : 0;
+    const bool is_a = local < a_tiles;
+    const long long c = is_a ? ph : ph - p.lag;
+    if (!is_a) local -= a_tiles;
+    const long long item0 = c * p.chunk;
+    if (is_a) {
+        if (p.slots && c >= p.slots) {
+            const long long cc = c - p.slots;
+            w.dep = p.done + p.nchunks + cc;
+            w.dep_target = (unsigned)(pipe_tilesum(p, cc + 1) - pipe_tilesum(p, cc));
+        }
+    } else {
+        w.dep = p.done + c;
+        w.dep_target = (unsigned)(pipe_tilesum(p, c + 1) - pipe_tilesum(p, c));
+    }
+    if (w.dep) { w.ready = ld_acquire_u32(w.dep) >= w.dep_target; __threadfence(); }
+    w.tile = item0 * p.tiles_per_item + local;
+    w.delta = p.slots ? (long long)(c % p.slots) * p.chunk - item0 : 0;
+    w.chunk = (int)c;
+    w.is_a = is_a ? 1 : 0;
+    return w;
+}
+
+__device__ __forceinline__ void pipe_wait(const PipeWork &w, int *error) {
+    if (!w.dep) return;
     unsigned spins = 0;
-    while (ld_acquire_u32(ctr) < target) {
+    while (ld_acquire_u32(w.dep) < w.dep_target) {
         napa_nanosleep(64);
         if (++spins > (1u << 24)) { *error = 1; break; }      // ~seconds: bail out instead of hanging the GPU
     }
@@ -484,62 +619,54 @@ __device__ __forceinline__ void pipe_wait(const unsigned *ctr, unsigned target, 
 }
 
 template <int LA, int LB>
+__device__ __forceinline__ void pipe_prefetch(const PipeParams &p, const PipeWork &w, cplx *sm) {
+    if (w.is_a) tile_prefetch<LA>(p.a, w.tile, sm, 0);
+    else tile_prefetch<LB>(p.b, w.tile, sm, p.b_src_is_ring ? w.delta : 0);
+}
+
+template <int LA, int LB>
 __global__ void __launch_bounds__(256, 2) fft_pipeline_kernel(const PipeParams p) {
     static_assert(plan_threads(LA) == 256 && plan_threads(LB) == 256, "pipeline passes use 256-thread tiles");
     NAPA_DYN_SMEM(cplx, sm);
-    __shared__ long long s_tile;       // global tile index of the decoded ticket, -1 = no more work
-    __shared__ long long s_delta;      // scratch-ring item delta
-    __shared__ int s_chunk, s_is_a;
+    __shared__ PipeWork s_cur, s_next;
+    __shared__ int s_cur_staged;
     const long long nphase = (long long)p.nchunks + p.lag;
     const long long total = pipe_prefix(p, nphase);
     long long next_ticket = 0;
-    if (threadIdx.x == 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+    if (threadIdx.x == 0) {
+        const long long tk = (long long)atomicAdd(p.ticket, 1ull);
+        PipeWork w = pipe_decode(p, tk, nphase, total);
+        if (w.tile >= 0) { pipe_wait(w, p.error); next_ticket = (long long)atomicAdd(p.ticket, 1ull); }
+        s_cur = w;
+        s_cur_staged = 0;
+    }
     for (;;) {
+        __syncthreads();                       // publishes s_cur; the previous tile is done with s_next
+        const PipeWork cur = s_cur;
+        if (cur.tile < 0) break;
+        const bool staged = s_cur_staged != 0;
         if (threadIdx.x == 0) {
-            // one thread decodes the ticket, waits for its dependencies and prefetches the next ticket
-            const long long tk = next_ticket;
-            if (tk >= total) {
-                s_tile = -1;
-            } else {
-                next_ticket = (long long)atomicAdd(p.ticket, 1ull);    // latency hidden behind this tile
-                long long lo = 0, hi = nphase;                         // phase = largest ph with prefix(ph) <= tk
-                while (hi - lo > 1) {
-                    const long long mid = (lo + hi) >> 1;
-                    if (pipe_prefix(p, mid) <= tk) lo = mid; else hi = mid;
-                }
-                const long long ph = lo;
-                long long local = tk - pipe_prefix(p, ph);
-                const long long a_tiles = ph < p.nchunks ? pipe_tilesum(p, ph + 1) - pipe_tilesum(p, ph) : 0;
-                const bool is_a = local < a_tiles;
-                const long long c = is_a ? ph : ph - p.lag;
-                if (!is_a) local -= a_tiles;
-                const long long item0 = c * p.chunk;
-                if (is_a) {
-                    if (p.slots && c >= p.slots) {
-                        const long long cc = c - p.slots;
-                        pipe_wait(p.done + p.nchunks + cc, (unsigned)(pipe_tilesum(p, cc + 1) - pipe_tilesum(p, cc)), p.error);
-                    }
-                } else {
-                    pipe_wait(p.done + c, (unsigned)(pipe_tilesum(p, c + 1) - pipe_tilesum(p, c)), p.error);
-                }
-                s_tile = item0 * p.tiles_per_item + local;
-                s_delta = p.slots ? (long long)(c % p.slots) * p.chunk - item0 : 0;
-                s_chunk = (int)c;
-                s_is_a = is_a ? 1 : 0;
-            }
+            // decode the ticket after this one; its prefetch is issued from the hook below
+            PipeWork w = pipe_decode(p, next_ticket, nphase, total);
+            if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);   // latency hidden behind this tile
+            s_next = w;
         }
-        __syncthreads();                       // publishes the ticket; previous tile is done with sm
-        const long long tile = s_tile;
-        if (tile < 0) break;
-        const long long delta = s_delta;
-        const int c = s_chunk;
-        const bool is_a = s_is_a != 0;
-        if (is_a) run_tile<LA, true>(p.a, tile, sm, 0, p.a_dst_is_ring ? delta : 0);
-        else run_tile<LB, true>(p.b, tile, sm, p.b_src_is_ring ? delta : 0, 0);
-        __syncthreads();                       // all stores of this tile issued; s_* may be rewritten
+        if (!staged) pipe_prefetch<LA, LB>(p, cur, sm);     // first tile of this CTA, or dependencies were late
+        auto hook = [&]() {
+            __syncthreads();                   // sm is free; s_next is visible
+            const PipeWork nx = s_next;
+            if (nx.tile >= 0 && nx.ready) pipe_prefetch<LA, LB>(p, nx, sm);
+        };
+        if (cur.is_a) run_tile<LA, true, true>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, hook);
+        else run_tile<LB, true, true>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, hook);
+        __syncthreads();                       // all stores of this tile issued
         if (threadIdx.x == 0) {
             __threadfence();
-            atomicAdd(p.done + (is_a ? 0 : p.nchunks) + c, 1u);
+            atomicAdd(p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk, 1u);
+            PipeWork nx = s_next;
+            if (nx.tile >= 0 && !nx.ready) pipe_wait(nx, p.error);
+            s_cur_staged = (nx.tile >= 0 && nx.ready) ? 1 : 0;
+            s_cur = nx;
         }
     }
 }

@@ -99,3 +99,19 @@ def test_batch_and_stride(napa):
         assert S.nre(spec[i], O.rfft(r[i])) <= S.tol(512)
     back = napa.rifft_batch(spec)
     assert S.nre(back, r) < 1e-12
+
+
+@pytest.mark.parametrize("n,batch", [(256, 300), (1024, 70), (4096, 17), (8192, 9), (64, 1100)])
+def test_persistent_single_pass(napa, n, batch):
+    """enough tiles that the launch goes persistent (cp.async-prefetched tile loop), incl. a ragged
+    last tile, the bit-reversed load path and a fused window"""
+    from oracle import napa_oracle as O
+    x = np.stack([S.rand_c(500 + i, n) for i in range(batch)])
+    w = S.rand_r(77, n, 1, 2)
+    got = napa.fft_batch(x.copy(), in_order=False, scale="sqrt", window=w)
+    back = napa.fft_batch(got.copy(), direction=-1, in_order=False, scale="sqrt")
+    for i in (0, 1, batch // 2, batch - 1):
+        want = O.fft(x[i], in_order=False, scale="sqrt", window=w)
+        assert S.nre(got[i], want) <= S.tol(n)
+        assert S.nre(back[i], O.ifft(want.copy(), in_order=False, scale="sqrt")) <= S.tol(n)
+    assert S.nre(back, x * w) < 1e-13
