@@ -293,6 +293,8 @@ static int launch_pipeline(int la, int lb, napa::PipeParams &pp, cudaStream_t st
     pp.ticket = (unsigned long long *)ctr;
     pp.done = (unsigned *)(ctr + 16);
     pp.error = G.d_error;
+    if (const char *env = getenv("NAPAFFT_DEBUG")) pp.debug = atoi(env);
+    if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
     const long long total_tiles = pp.items * pp.tiles_per_item * 2;
     long long grid = std::min<long long>((long long)G.num_sms * it->second, total_tiles);
     NAPA_LAUNCH(fn, (unsigned)grid, 256, smem, st, pp);

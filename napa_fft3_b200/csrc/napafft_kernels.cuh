@@ -368,9 +368,9 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 // (cp.async.cg: L2-coherent, no register staging).  The same thread gathers them later, so the
 // only synchronisation needed is cp.async.wait_group by that thread.
 template <int LOG2L>
-__device__ __forceinline__ void tile_prefetch(const PassParams &p, const long long tile, cplx *sm, const long long src_item_delta) {
+__device__ __forceinline__ void tile_prefetch(const PassParams &p, const long long tile, cplx *sm, const long long src_item_delta,
+                                              const L2Policies &pol) {
     constexpr int T = (1 << LOG2L) / 16;
-    const L2Policies pol = make_policies();
     const TileCtx c = tile_ctx<LOG2L>(p, tile);
     if (c.valid) {
         const cplx *src = p.src + (c.item + src_item_delta) * p.src_batch_stride + c.s_xoff;
@@ -399,11 +399,11 @@ __device__ __forceinline__ void tile_prefetch(const PassParams &p, const long lo
 // nothing and used ones do not serialise the loads.
 template <int LOG2L, bool COHERENT, bool STAGED, class Hook>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
-                                         const long long src_item_delta, const long long dst_item_delta, Hook &hook) {
+                                         const long long src_item_delta, const long long dst_item_delta, Hook &hook,
+                                         const L2Policies &pol) {
     constexpr int L = 1 << LOG2L;
     constexpr int T = L / 16;
     static_assert(!STAGED || plan_nstages(LOG2L) > 1, "staging needs a shared-memory buffer");
-    const L2Policies pol = make_policies();
     const int src_hint = p.src_hint, dst_hint = p.dst_hint;
     const TileCtx c = tile_ctx<LOG2L>(p, tile);
     const int t = c.t, q = c.q;
@@ -504,18 +504,19 @@ template <int LOG2L>
 __global__ void __launch_bounds__(plan_threads(LOG2L), (plan_threads(LOG2L) <= 256 ? 2 : 1))
 fft_pass_kernel(const PassParams p, const long long ntiles, const int persist) {
     NAPA_DYN_SMEM(cplx, sm);
+    const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     if constexpr (plan_nstages(LOG2L) > 1) {
         if (persist) {
             long long tile = blockIdx.x;
             if (tile >= ntiles) return;
-            tile_prefetch<LOG2L>(p, tile, sm, 0);
+            tile_prefetch<LOG2L>(p, tile, sm, 0, pol);
             for (;;) {
                 const long long next = tile + gridDim.x;
                 auto hook = [&]() {
                     __syncthreads();                       // sm is free: everyone gathered the last exchange
-                    if (next < ntiles) tile_prefetch<LOG2L>(p, next, sm, 0);
+                    if (next < ntiles) tile_prefetch<LOG2L>(p, next, sm, 0, pol);
                 };
-                run_tile<LOG2L, false, true>(p, tile, sm, 0, 0, hook);
+                run_tile<LOG2L, false, true>(p, tile, sm, 0, 0, hook, pol);
                 if (next >= ntiles) break;
                 tile = next;
             }
@@ -523,7 +524,7 @@ fft_pass_kernel(const PassParams p, const long long ntiles, const int persist) {
         }
     }
     NoHook nh;
-    run_tile<LOG2L, false, false>(p, (long long)blockIdx.x, sm, 0, 0, nh);
+    run_tile<LOG2L, false, false>(p, (long long)blockIdx.x, sm, 0, 0, nh, pol);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -551,6 +552,7 @@ struct PipeParams {
     unsigned long long *ticket;      // zeroed before launch
     unsigned *done;                  // [2][nchunks], zeroed before launch
     int *error;                      // set to 1 if a wait timed out (never expected)
+    int debug;                       // bit0: no hook prefetch
 };
 
 __device__ __forceinline__ long long pipe_tilesum(const PipeParams &p, long long k) {
@@ -619,9 +621,9 @@ __device__ __forceinline__ void pipe_wait(const PipeWork &w, int *error) {
 }
 
 template <int LA, int LB>
-__device__ __forceinline__ void pipe_prefetch(const PipeParams &p, const PipeWork &w, cplx *sm) {
-    if (w.is_a) tile_prefetch<LA>(p.a, w.tile, sm, 0);
-    else tile_prefetch<LB>(p.b, w.tile, sm, p.b_src_is_ring ? w.delta : 0);
+__device__ __forceinline__ void pipe_prefetch(const PipeParams &p, const PipeWork &w, cplx *sm, const L2Policies &pol) {
+    if (w.is_a) tile_prefetch<LA>(p.a, w.tile, sm, 0, pol);
+    else tile_prefetch<LB>(p.b, w.tile, sm, p.b_src_is_ring ? w.delta : 0, pol);
 }
 
 template <int LA, int LB>
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(256, 2) fft_pipeline_kernel(const PipeParams p
     NAPA_DYN_SMEM(cplx, sm);
     __shared__ PipeWork s_cur, s_next;
     __shared__ int s_cur_staged;
+    const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     const long long nphase = (long long)p.nchunks + p.lag;
     const long long total = pipe_prefix(p, nphase);
     long long next_ticket = 0;
@@ -651,21 +654,21 @@ __global__ void __launch_bounds__(256, 2) fft_pipeline_kernel(const PipeParams p
             if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);   // latency hidden behind this tile
             s_next = w;
         }
-        if (!staged) pipe_prefetch<LA, LB>(p, cur, sm);     // first tile of this CTA, or dependencies were late
+        if (!staged) pipe_prefetch<LA, LB>(p, cur, sm, pol);     // first tile of this CTA, or dependencies were late
         auto hook = [&]() {
             __syncthreads();                   // sm is free; s_next is visible
             const PipeWork nx = s_next;
-            if (nx.tile >= 0 && nx.ready) pipe_prefetch<LA, LB>(p, nx, sm);
+            if (nx.tile >= 0 && nx.ready && !(p.debug & 1)) pipe_prefetch<LA, LB>(p, nx, sm, pol);
         };
-        if (cur.is_a) run_tile<LA, true, true>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, hook);
-        else run_tile<LB, true, true>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, hook);
+        if (cur.is_a) run_tile<LA, true, true>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, hook, pol);
+        else run_tile<LB, true, true>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, hook, pol);
         __syncthreads();                       // all stores of this tile issued
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk, 1u);
             PipeWork nx = s_next;
             if (nx.tile >= 0 && !nx.ready) pipe_wait(nx, p.error);
-            s_cur_staged = (nx.tile >= 0 && nx.ready) ? 1 : 0;
+            s_cur_staged = (nx.tile >= 0 && nx.ready && !(p.debug & 1)) ? 1 : 0;
             s_cur = nx;
         }
     }
