@@ -229,7 +229,7 @@ static int launch_pass(int l, PassParams &p, long long ntiles, cudaStream_t st) 
     if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
     pass_fn fn = pass_kernel(l);
     // big launches of exchange-bearing sizes run persistent CTAs with cp.async prefetch
-    const long long resident = (long long)G.num_sms * (napa::plan_threads(l) <= 256 ? 2 : 1);
+    const long long resident = (long long)G.num_sms * napa::plan_min_ctas(l);
     const int persist = G.use_persist && napa::plan_nstages(l) > 1 && ntiles >= 4 * resident ? 1 : 0;
     const long long grid = persist ? resident : ntiles;
     NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p, ntiles, persist);
@@ -242,7 +242,10 @@ typedef void (*pipe_fn)(const napa::PipeParams);
 #define NAPA_PIPE_CASE(a, b) if (la == a && lb == b) return napa::fft_pipeline_kernel<a, b>;
 static pipe_fn pipe_kernel(int la, int lb) {
     NAPA_PIPE_CASE(7, 7) NAPA_PIPE_CASE(7, 8) NAPA_PIPE_CASE(8, 7) NAPA_PIPE_CASE(8, 8)
-    NAPA_PIPE_CASE(8, 9) NAPA_PIPE_CASE(9, 8) NAPA_PIPE_CASE(9, 9) NAPA_PIPE_CASE(9, 10)
+#if NAPA_SMALL_TILE_MAXL != 8
+    NAPA_PIPE_CASE(8, 9) NAPA_PIPE_CASE(9, 8)
+#endif
+    NAPA_PIPE_CASE(9, 9) NAPA_PIPE_CASE(9, 10)
     NAPA_PIPE_CASE(10, 9) NAPA_PIPE_CASE(10, 10) NAPA_PIPE_CASE(10, 11) NAPA_PIPE_CASE(11, 10)
     NAPA_PIPE_CASE(10, 12) NAPA_PIPE_CASE(12, 10)
     return nullptr;
@@ -282,7 +285,7 @@ static int launch_pipeline(int la, int lb, napa::PipeParams &pp, cudaStream_t st
     if (it == occupancy.end()) {
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, 256, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la), smem));
         if (nb < 1) return fail(NAPA_E_CUDA, "pipeline kernel does not fit on an SM");
         it = occupancy.emplace(fn, nb).first;
     }
@@ -297,7 +300,7 @@ static int launch_pipeline(int la, int lb, napa::PipeParams &pp, cudaStream_t st
     if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
     const long long total_tiles = pp.items * pp.tiles_per_item * 2;
     long long grid = std::min<long long>((long long)G.num_sms * it->second, total_tiles);
-    NAPA_LAUNCH(fn, (unsigned)grid, 256, smem, st, pp);
+    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la), smem, st, pp);
     g_launches++;
     return NAPA_OK;
 }
@@ -416,14 +419,15 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     chunk = std::min(chunk, batch);
 
     const bool natural = o.in_order != 0;
-    const bool can_pipe = G.use_pipeline && p == 2 && d[0] <= 12 && d[1] <= 12;
+    const bool can_pipe = G.use_pipeline && p == 2 && d[0] <= 12 && d[1] <= 12 &&
+                          napa::plan_log2pts(d[0]) == napa::plan_log2pts(d[1]);   // one tile shape per pipeline
     if (can_pipe) {
         napa::PipeParams pp{};
         size_t pchunk = std::max<size_t>(1, G.pipe_chunk_bytes / (n * sizeof(cplx)));
         pchunk = std::min(pchunk, batch);
         pp.items = (long long)batch; pp.chunk = (int)pchunk; pp.nchunks = (int)((batch + pchunk - 1) / pchunk);
         pp.lag = std::max(1, G.pipe_lag);
-        pp.tiles_per_item = (long long)(n >> 12);
+        pp.tiles_per_item = (long long)(n >> napa::plan_log2pts(d[0]));
         long long tpi;
         if (natural) {
             // A: column pass src -> scratch ring (+ inter-pass twiddle); B: row pass ring -> dst, transposed store

@@ -132,8 +132,13 @@ __host__ __device__ constexpr int plan_log2radix(int l, int s) {
     }
     return 0;
 }
-// tile shape: C*L = 4096 points per CTA (8192 for L = 8192); 16 points per thread
-__host__ __device__ constexpr int plan_log2c(int l) { return l <= 12 ? 12 - l : 0; }
+// tile shape: C*L = 2048 / 4096 / 8192 points per CTA; 16 points per thread
+#ifndef NAPA_SMALL_TILE_MAXL
+#define NAPA_SMALL_TILE_MAXL 8     // L <= 2^8: 2048-point tiles on 128 threads (4 CTAs/SM, more barrier domains)
+#endif
+__host__ __device__ constexpr int plan_log2pts(int l) { return l <= NAPA_SMALL_TILE_MAXL ? 11 : (l <= 12 ? 12 : 13); }
+__host__ __device__ constexpr int plan_log2c(int l) { return plan_log2pts(l) - l; }
+__host__ __device__ constexpr int plan_min_ctas(int l) { return plan_log2pts(l) == 11 ? 4 : (plan_log2pts(l) == 12 ? 2 : 1); }
 __host__ __device__ constexpr int plan_threads(int l) { return (1 << (l - 4)) << plan_log2c(l); }
 // shared-memory index padding (only needed when C < 8; see tools/bank_check.py)
 __host__ __device__ constexpr int plan_padshift(int l) { return plan_log2c(l) >= 3 ? 31 : 4; }
@@ -196,21 +201,21 @@ __device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int, const L2
 __device__ __forceinline__ void cp_async_commit() {}
 __device__ __forceinline__ void cp_async_wait_all() {}
 #else
-struct L2Policies { unsigned long long first, last; };
+struct L2Policies { unsigned long long normal, first, last; };
 __device__ __forceinline__ L2Policies make_policies() {
     L2Policies pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol.normal));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol.first));
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol.last));
     return pol;
 }
+__device__ __forceinline__ unsigned long long pick_policy(const L2Policies &pol, int hint) {
+    return hint == HINT_STREAM ? pol.first : (hint == HINT_KEEP ? pol.last : pol.normal);
+}
 // COHERENT: L2-only (.cg) because another SM may have written the line earlier in this launch
 template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, int hint, const L2Policies &pol) {
     cplx v;
-    if (hint == HINT_NORMAL) {
-        if (COHERENT) return __ldcg(p);
-        return *p;
-    }
-    const unsigned long long policy = hint == HINT_STREAM ? pol.first : pol.last;
+    const unsigned long long policy = pick_policy(pol, hint);
     if (COHERENT)
         asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy) : "memory");
     else
@@ -218,8 +223,7 @@ template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, 
     return v;
 }
 __device__ __forceinline__ void st_data(cplx *p, cplx v, int hint, const L2Policies &pol) {
-    if (hint == HINT_NORMAL) { *p = v; return; }
-    const unsigned long long policy = hint == HINT_STREAM ? pol.first : pol.last;
+    const unsigned long long policy = pick_policy(pol, hint);
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
@@ -231,12 +235,8 @@ __device__ __forceinline__ void napa_nanosleep(unsigned ns) { __nanosleep(ns); }
 // 16-byte asynchronous global->shared copy, L2-only (.cg) hence coherent with other SMs' writes
 __device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int hint, const L2Policies &pol) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
-    if (hint == HINT_NORMAL) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
-    } else {
-        const unsigned long long policy = hint == HINT_STREAM ? pol.first : pol.last;
-        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(sa), "l"(g), "l"(policy) : "memory");
-    }
+    const unsigned long long policy = pick_policy(pol, hint);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(sa), "l"(g), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -411,11 +411,22 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     const long long s_xoff = c.s_xoff;
 
     cplx v[16];
-    if (STAGED) cp_async_wait_all();
     if (c.valid) {
         const cplx *src = p.src + (c.item + src_item_delta) * p.src_batch_stride + s_xoff;
         const long long s_i = p.s_i;
+        // real window values are fetched first: they do not depend on the data and their L2
+        // latency then overlaps the data wait
+        double wv[16];
+        if (flags & PF_WIN_REAL) {
+            const double *w = reinterpret_cast<const double *>(p.window) + c.item * p.window_batch_stride;
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + m * T, LOG2L) : t + m * T) * s_i;
+                wv[m] = __ldg(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
+            }
+        }
         if (STAGED) {
+            cp_async_wait_all();
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L>(t + m * T, q)];
         } else if (flags & PF_IN_REV) {
@@ -440,31 +451,23 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = cscale(v[m], sc);
         }
-        if (flags & (PF_WIN_REAL | PF_WIN_CPLX)) {
-            const long long wbase = c.item * p.window_batch_stride;
-            long long widx[16];
+        if (flags & PF_WIN_REAL) {
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + m * T, LOG2L) : t + m * T) * s_i;
-                widx[m] = wbase + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off);
-            }
-            if (flags & PF_WIN_REAL) {
-                const double *w = reinterpret_cast<const double *>(p.window);
-                double wv[16];
+            for (int m = 0; m < 16; m++) v[m] = cscale(v[m], wv[m]);
+        }
+        if (flags & PF_WIN_CPLX) {
+            const cplx *w = reinterpret_cast<const cplx *>(p.window) + c.item * p.window_batch_stride;
 #pragma unroll
-                for (int m = 0; m < 16; m++) wv[m] = __ldg(w + widx[m]);
+            for (int h = 0; h < 2; h++) {
+                cplx wc[8];
 #pragma unroll
-                for (int m = 0; m < 16; m++) v[m] = cscale(v[m], wv[m]);
-            } else {
-                const cplx *w = reinterpret_cast<const cplx *>(p.window);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    cplx wv[8];
-#pragma unroll
-                    for (int m = 0; m < 8; m++) wv[m] = ldg_c(w + widx[8 * h + m]);
-#pragma unroll
-                    for (int m = 0; m < 8; m++) v[8 * h + m] = cmul(v[8 * h + m], wv[m]);
+                for (int m = 0; m < 8; m++) {
+                    const int mm = 8 * h + m;
+                    const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + mm * T, LOG2L) : t + mm * T) * s_i;
+                    wc[m] = ldg_c(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
                 }
+#pragma unroll
+                for (int m = 0; m < 8; m++) v[8 * h + m] = cmul(v[8 * h + m], wc[m]);
             }
         }
         if (flags & PF_CONJ_IN) {
@@ -473,6 +476,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         }
         if (flags & PF_TW_LOAD) apply_big_twiddle<T>(v, p, t, c.col);
     } else {
+        if (STAGED) cp_async_wait_all();
 #pragma unroll
         for (int m = 0; m < 16; m++) v[m] = make_double2(0.0, 0.0);
     }
@@ -501,7 +505,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 // registers.  Large launches (persist != 0): persistent CTAs walk tiles blockIdx.x, +gridDim.x, ...
 // and prefetch the next tile with cp.async while the last radix stage of the current one runs.
 template <int LOG2L>
-__global__ void __launch_bounds__(plan_threads(LOG2L), (plan_threads(LOG2L) <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(plan_threads(LOG2L), plan_min_ctas(LOG2L))
 fft_pass_kernel(const PassParams p, const long long ntiles, const int persist) {
     NAPA_DYN_SMEM(cplx, sm);
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
@@ -627,8 +631,8 @@ __device__ __forceinline__ void pipe_prefetch(const PipeParams &p, const PipeWor
 }
 
 template <int LA, int LB>
-__global__ void __launch_bounds__(256, 2) fft_pipeline_kernel(const PipeParams p) {
-    static_assert(plan_threads(LA) == 256 && plan_threads(LB) == 256, "pipeline passes use 256-thread tiles");
+__global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
+    static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
     NAPA_DYN_SMEM(cplx, sm);
     __shared__ PipeWork s_cur, s_next;
     __shared__ int s_cur_staged;
