@@ -77,7 +77,7 @@ struct State {
     size_t pipe_chunk_bytes = 8u << 20;   // chunk of the persistent pipeline
     int pipe_lag = 3;                     // phases between the two passes of a chunk
     bool use_pipeline = true;
-    bool use_persist = true;
+    bool use_persist = false;   // cp.async-staged persistent single-pass loop: measured slower than one tile per CTA
     bool attrs_set = false;
     int num_sms = 148;
     std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream ticket/done block
@@ -805,7 +805,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
     if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
-    if (const char *env = getenv("NAPAFFT_NO_PERSIST")) G.use_persist = atoi(env) == 0;
+    if (const char *env = getenv("NAPAFFT_PERSIST")) G.use_persist = atoi(env) != 0;
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;

@@ -635,7 +635,6 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipel
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
     NAPA_DYN_SMEM(cplx, sm);
     __shared__ PipeWork s_cur, s_next;
-    __shared__ int s_cur_staged;
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     const long long nphase = (long long)p.nchunks + p.lag;
     const long long total = pipe_prefix(p, nphase);
@@ -645,34 +644,26 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipel
         PipeWork w = pipe_decode(p, tk, nphase, total);
         if (w.tile >= 0) { pipe_wait(w, p.error); next_ticket = (long long)atomicAdd(p.ticket, 1ull); }
         s_cur = w;
-        s_cur_staged = 0;
     }
     for (;;) {
         __syncthreads();                       // publishes s_cur; the previous tile is done with s_next
         const PipeWork cur = s_cur;
         if (cur.tile < 0) break;
-        const bool staged = s_cur_staged != 0;
         if (threadIdx.x == 0) {
             // decode the ticket after this one; its prefetch is issued from the hook below
             PipeWork w = pipe_decode(p, next_ticket, nphase, total);
             if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);   // latency hidden behind this tile
             s_next = w;
         }
-        if (!staged) pipe_prefetch<LA, LB>(p, cur, sm, pol);     // first tile of this CTA, or dependencies were late
-        auto hook = [&]() {
-            __syncthreads();                   // sm is free; s_next is visible
-            const PipeWork nx = s_next;
-            if (nx.tile >= 0 && nx.ready && !(p.debug & 1)) pipe_prefetch<LA, LB>(p, nx, sm, pol);
-        };
-        if (cur.is_a) run_tile<LA, true, true>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, hook, pol);
-        else run_tile<LB, true, true>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, hook, pol);
+        NoHook hook;
+        if (cur.is_a) run_tile<LA, true, false>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, hook, pol);
+        else run_tile<LB, true, false>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, hook, pol);
         __syncthreads();                       // all stores of this tile issued
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk, 1u);
             PipeWork nx = s_next;
             if (nx.tile >= 0 && !nx.ready) pipe_wait(nx, p.error);
-            s_cur_staged = (nx.tile >= 0 && nx.ready && !(p.debug & 1)) ? 1 : 0;
             s_cur = nx;
         }
     }
