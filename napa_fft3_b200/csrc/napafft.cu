@@ -77,6 +77,7 @@ struct State {
     size_t pipe_chunk_bytes = 8u << 20;   // chunk of the persistent pipeline
     int pipe_lag = 3;                     // phases between the two passes of a chunk
     bool use_pipeline = true;
+    int pf_dist_waves = 1;                // one-tile-per-CTA launches prefetch the tile `waves * resident CTAs` ahead into L2
     bool use_persist = false;   // cp.async-staged persistent single-pass loop: measured slower than one tile per CTA
     bool attrs_set = false;
     int num_sms = 148;
@@ -194,7 +195,7 @@ static int ensure_scratch(size_t bytes) {
 // ------------------------------------------------------------------------------------------
 // kernel launch table
 // ------------------------------------------------------------------------------------------
-typedef void (*pass_fn)(const PassParams, const long long, const int);
+typedef void (*pass_fn)(const PassParams, const long long, const int, const int);
 static pass_fn pass_kernel(int l) {
     switch (l) {
     case 4: return napa::fft_pass_kernel<4>;
@@ -232,7 +233,8 @@ static int launch_pass(int l, PassParams &p, long long ntiles, cudaStream_t st) 
     const long long resident = (long long)G.num_sms * napa::plan_min_ctas(l);
     const int persist = G.use_persist && napa::plan_nstages(l) > 1 && ntiles >= 4 * resident ? 1 : 0;
     const long long grid = persist ? resident : ntiles;
-    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p, ntiles, persist);
+    const int pf_dist = G.pf_dist_waves > 0 && !persist ? (int)(resident * G.pf_dist_waves) : 0;
+    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p, ntiles, persist, pf_dist);
     g_launches++;
     return NAPA_OK;
 }
@@ -806,6 +808,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
     if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
     if (const char *env = getenv("NAPAFFT_PERSIST")) G.use_persist = atoi(env) != 0;
+    if (const char *env = getenv("NAPAFFT_PF_WAVES")) G.pf_dist_waves = atoi(env);
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;

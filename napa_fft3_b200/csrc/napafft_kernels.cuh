@@ -200,6 +200,7 @@ __device__ __forceinline__ void napa_nanosleep(unsigned) {}
 __device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int, const L2Policies &) { *s = *g; }
 __device__ __forceinline__ void cp_async_commit() {}
 __device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void l2_prefetch(const void *) {}
 #else
 struct L2Policies { unsigned long long normal, first, last; };
 __device__ __forceinline__ L2Policies make_policies() {
@@ -238,6 +239,7 @@ __device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int hint, con
     const unsigned long long policy = pick_policy(pol, hint);
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(sa), "l"(g), "l"(policy) : "memory");
 }
+__device__ __forceinline__ void l2_prefetch(const void *g) { asm volatile("prefetch.global.L2 [%0];" :: "l"(g)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #endif
@@ -389,6 +391,25 @@ __device__ __forceinline__ void tile_prefetch(const PassParams &p, const long lo
     cp_async_commit();
 }
 
+// Software L2 prefetch of a whole tile: one prefetch.global.L2 per 128-byte line (issued by the
+// thread that owns the line's first element).  It costs no registers and no shared memory, so it
+// adds bytes in flight beyond what register-staged loads can hold (memory-level parallelism is
+// what bounds the HBM-facing pass).
+template <int LOG2L>
+__device__ __forceinline__ void tile_l2_prefetch(const PassParams &p, const long long tile) {
+    constexpr int T = (1 << LOG2L) / 16;
+    const TileCtx c = tile_ctx<LOG2L>(p, tile);
+    if (!c.valid) return;
+    const cplx *src = p.src + c.item * p.src_batch_stride + c.s_xoff;
+    const long long s_i = p.s_i;
+    const bool rev = (p.flags & PF_IN_REV) != 0;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const cplx *a = src + (long long)(rev ? rev_bits(c.t + m * T, LOG2L) : c.t + m * T) * s_i;
+        if ((reinterpret_cast<unsigned long long>(a) & 127ull) == 0) l2_prefetch(a);
+    }
+}
+
 // One tile of one digit pass.  COHERENT selects L2-only (ld.global.cg) data loads: required when
 // the data was written earlier in the SAME launch by another SM (persistent pipeline), where a
 // stale L1 line would be a bug.  STAGED: the input was prefetched into sm by tile_prefetch.
@@ -506,9 +527,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 // and prefetch the next tile with cp.async while the last radix stage of the current one runs.
 template <int LOG2L>
 __global__ void __launch_bounds__(plan_threads(LOG2L), plan_min_ctas(LOG2L))
-fft_pass_kernel(const PassParams p, const long long ntiles, const int persist) {
+fft_pass_kernel(const PassParams p, const long long ntiles, const int persist, const int pf_dist) {
     NAPA_DYN_SMEM(cplx, sm);
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
+    if (pf_dist > 0 && (long long)blockIdx.x + pf_dist < ntiles) tile_l2_prefetch<LOG2L>(p, (long long)blockIdx.x + pf_dist);
     if constexpr (plan_nstages(LOG2L) > 1) {
         if (persist) {
             long long tile = blockIdx.x;
@@ -634,26 +656,37 @@ template <int LA, int LB>
 __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
     NAPA_DYN_SMEM(cplx, sm);
-    __shared__ PipeWork s_cur, s_next;
+    __shared__ PipeWork s_work[3];                   // ring: current tile, next tile, the one being decoded
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     const long long nphase = (long long)p.nchunks + p.lag;
     const long long total = pipe_prefix(p, nphase);
     long long next_ticket = 0;
     if (threadIdx.x == 0) {
-        const long long tk = (long long)atomicAdd(p.ticket, 1ull);
-        PipeWork w = pipe_decode(p, tk, nphase, total);
-        if (w.tile >= 0) { pipe_wait(w, p.error); next_ticket = (long long)atomicAdd(p.ticket, 1ull); }
-        s_cur = w;
+        // tickets of this CTA are decoded two tiles ahead: slot k%3 = tile k
+        PipeWork w0 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
+        PipeWork w1 = w0;
+        w1.tile = -1;
+        if (w0.tile >= 0) w1 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
+        if (w1.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+        if (w0.tile >= 0 && !w0.ready) pipe_wait(w0, p.error);
+        s_work[0] = w0;
+        s_work[1] = w1;
     }
-    for (;;) {
-        __syncthreads();                       // publishes s_cur; the previous tile is done with s_next
-        const PipeWork cur = s_cur;
+    for (int k = 0;; k++) {
+        __syncthreads();                       // publishes slots k%3 and (k+1)%3; slot (k+2)%3 is free
+        const PipeWork cur = s_work[k % 3];
         if (cur.tile < 0) break;
+        const PipeWork nxt = s_work[(k + 1) % 3];
+        // the HBM-facing pass (A reads the caller's src) gets its next tile pulled into L2 now
+        if (nxt.tile >= 0 && nxt.is_a && !(p.debug & 4)) tile_l2_prefetch<LA>(p.a, nxt.tile);
         if (threadIdx.x == 0) {
-            // decode the ticket after this one; its prefetch is issued from the hook below
-            PipeWork w = pipe_decode(p, next_ticket, nphase, total);
-            if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);   // latency hidden behind this tile
-            s_next = w;
+            PipeWork w;
+            w.tile = -1;
+            if (nxt.tile >= 0) {
+                w = pipe_decode(p, next_ticket, nphase, total);
+                if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);   // latency hidden behind this tile
+            }
+            s_work[(k + 2) % 3] = w;
         }
         NoHook hook;
         if (cur.is_a) run_tile<LA, true, false>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, hook, pol);
@@ -662,9 +695,7 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipel
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk, 1u);
-            PipeWork nx = s_next;
-            if (nx.tile >= 0 && !nx.ready) pipe_wait(nx, p.error);
-            s_cur = nx;
+            if (nxt.tile >= 0 && !nxt.ready) pipe_wait(nxt, p.error);   // dependencies of the next tile (rarely late)
         }
     }
 }
