@@ -257,6 +257,36 @@ __device__ __forceinline__ int smem_phys(int pos, int q) {
 
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
+// v[u + s*NB] *= w^s for s = 1 .. R-1
+template <int R, int NB>
+__device__ __forceinline__ void twiddle_powers(cplx (&v)[16], const int u, const cplx w1) {
+    if constexpr (R >= 2) v[u + 1 * NB] = cmul(v[u + 1 * NB], w1);
+    if constexpr (R >= 4) {
+        const cplx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+        v[u + 2 * NB] = cmul(v[u + 2 * NB], w2);
+        v[u + 3 * NB] = cmul(v[u + 3 * NB], w3);
+        if constexpr (R >= 8) {
+            const cplx w4 = cmul(w2, w2);
+            const cplx w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+            v[u + 4 * NB] = cmul(v[u + 4 * NB], w4);
+            v[u + 5 * NB] = cmul(v[u + 5 * NB], w5);
+            v[u + 6 * NB] = cmul(v[u + 6 * NB], w6);
+            v[u + 7 * NB] = cmul(v[u + 7 * NB], w7);
+            if constexpr (R >= 16) {
+                const cplx w8 = cmul(w4, w4);
+                v[u + 8 * NB] = cmul(v[u + 8 * NB], w8);
+                v[u + 9 * NB] = cmul(v[u + 9 * NB], cmul(w8, w1));
+                v[u + 10 * NB] = cmul(v[u + 10 * NB], cmul(w8, w2));
+                v[u + 11 * NB] = cmul(v[u + 11 * NB], cmul(w8, w3));
+                v[u + 12 * NB] = cmul(v[u + 12 * NB], cmul(w8, w4));
+                v[u + 13 * NB] = cmul(v[u + 13 * NB], cmul(w8, w5));
+                v[u + 14 * NB] = cmul(v[u + 14 * NB], cmul(w8, w6));
+                v[u + 15 * NB] = cmul(v[u + 15 * NB], cmul(w8, w7));
+            }
+        }
+    }
+}
+
 // PRESYNC0: the tile's input was staged in sm (thread-private slots); everyone must have read its
 // staged input before stage 0 scatters.  `hook` runs right after the gather of the LAST stage, i.e.
 // at the first moment sm is free again (used to issue the next tile's cp.async prefetch).
@@ -276,15 +306,14 @@ struct Stages {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L>(t + m * T, q)];
             if constexpr (STAGE + 1 == NSTAGES) hook();
-            // twiddle W_{NS*R}^{(jb % NS) * s} on input s of butterfly jb = t + u*T
+            // twiddle W_{NS*R}^{(jb % NS) * s} on input s of butterfly jb = t + u*T.  Only the seed
+            // w = W^{jb % NS} is loaded; its powers come from a product tree (depth <= 4): the
+            // LSU<->register datapath, not the FP64 pipe, is the scarce resource of this kernel.
 #pragma unroll
             for (int u = 0; u < NB; u++) {
-                int jm = (t + u * T) & (NS - 1);
-#pragma unroll
-                for (int s = 1; s < R; s++) {
-                    cplx w = ldg_c(tw + (jm * s) * (L / (NS * R)));
-                    v[u + s * NB] = cmul(v[u + s * NB], w);
-                }
+                const int jm = (t + u * T) & (NS - 1);
+                const cplx w1 = ldg_c(tw + jm * (L / (NS * R)));
+                twiddle_powers<R, NB>(v, u, w1);
             }
         }
 #pragma unroll
