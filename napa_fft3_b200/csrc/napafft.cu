@@ -77,8 +77,6 @@ struct State {
     size_t pipe_chunk_bytes = 8u << 20;   // chunk of the persistent pipeline
     int pipe_lag = 3;                     // phases between the two passes of a chunk
     bool use_pipeline = true;
-    int pf_dist_waves = 1;                // one-tile-per-CTA launches prefetch the tile `waves * resident CTAs` ahead into L2
-    bool use_persist = false;   // cp.async-staged persistent single-pass loop: measured slower than one tile per CTA
     bool attrs_set = false;
     int num_sms = 148;
     std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream ticket/done block
@@ -195,58 +193,59 @@ static int ensure_scratch(size_t bytes) {
 // ------------------------------------------------------------------------------------------
 // kernel launch table
 // ------------------------------------------------------------------------------------------
-typedef void (*pass_fn)(const PassParams, const long long, const int, const int);
-static pass_fn pass_kernel(int l) {
+// tile kinds (lane maps): 0 column-like, 1 row-like, 2 row-like load + transposed store
+enum { KIND_COL = 0, KIND_ROW = 1, KIND_ROWT = 2 };
+typedef void (*pass_fn)(const PassParams);
+template <int K> static pass_fn pass_kernel_k(int l) {
     switch (l) {
-    case 4: return napa::fft_pass_kernel<4>;
-    case 5: return napa::fft_pass_kernel<5>;
-    case 6: return napa::fft_pass_kernel<6>;
-    case 7: return napa::fft_pass_kernel<7>;
-    case 8: return napa::fft_pass_kernel<8>;
-    case 9: return napa::fft_pass_kernel<9>;
-    case 10: return napa::fft_pass_kernel<10>;
-    case 11: return napa::fft_pass_kernel<11>;
-    case 12: return napa::fft_pass_kernel<12>;
-    case 13: return napa::fft_pass_kernel<13>;
+    case 4: return napa::fft_pass_kernel<4, K>;
+    case 5: return napa::fft_pass_kernel<5, K>;
+    case 6: return napa::fft_pass_kernel<6, K>;
+    case 7: return napa::fft_pass_kernel<7, K>;
+    case 8: return napa::fft_pass_kernel<8, K>;
+    case 9: return napa::fft_pass_kernel<9, K>;
+    case 10: return napa::fft_pass_kernel<10, K>;
+    case 11: return napa::fft_pass_kernel<11, K>;
+    case 12: return napa::fft_pass_kernel<12, K>;
+    case 13: return napa::fft_pass_kernel<13, K>;
     }
     return nullptr;
+}
+static pass_fn pass_kernel(int l, int kind) {
+    if (l < 7) kind = KIND_COL;            // small L: one lane map (see kind_lm)
+    return kind == KIND_COL ? pass_kernel_k<0>(l) : (kind == KIND_ROW ? pass_kernel_k<1>(l) : pass_kernel_k<2>(l));
 }
 
 static int set_kernel_attrs() {
     if (G.attrs_set) return NAPA_OK;
-    for (int l = 4; l <= 13; l++) {
-        size_t sm = napa::plan_smem_bytes(l);
-        if (sm > 48 * 1024)
-            CU(cudaFuncSetAttribute((const void *)pass_kernel(l), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    }
+    for (int l = 4; l <= 13; l++)
+        for (int kind = 0; kind < 3; kind++) {
+            size_t sm = napa::kind_smem_bytes(l, kind);
+            if (sm > 48 * 1024)
+                CU(cudaFuncSetAttribute((const void *)pass_kernel(l, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        }
     G.attrs_set = true;
     return NAPA_OK;
 }
 
-static int launch_pass(int l, PassParams &p, long long ntiles, cudaStream_t st) {
+static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStream_t st) {
     OK(ensure_stage_tw(l));
     p.stage_tw = G.stage_tw[l];
     if (ntiles <= 0) return NAPA_OK;
     if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
-    pass_fn fn = pass_kernel(l);
-    // big launches of exchange-bearing sizes run persistent CTAs with cp.async prefetch
-    const long long resident = (long long)G.num_sms * napa::plan_min_ctas(l);
-    const int persist = G.use_persist && napa::plan_nstages(l) > 1 && ntiles >= 4 * resident ? 1 : 0;
-    const long long grid = persist ? resident : ntiles;
-    const int pf_dist = G.pf_dist_waves > 0 && !persist ? (int)(resident * G.pf_dist_waves) : 0;
-    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(l), napa::plan_smem_bytes(l), st, p, ntiles, persist, pf_dist);
+    pass_fn fn = pass_kernel(l, kind);
+    NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::kind_smem_bytes(l, l < 7 ? 0 : kind), st, p);
     g_launches++;
     return NAPA_OK;
 }
 
-// persistent two-pass pipeline kernels: (first-executed digit, second digit)
+// persistent two-pass pipeline kernels: (first-executed digit, second digit, pipeline kind)
 typedef void (*pipe_fn)(const napa::PipeParams);
-#define NAPA_PIPE_CASE(a, b) if (la == a && lb == b) return napa::fft_pipeline_kernel<a, b>;
-static pipe_fn pipe_kernel(int la, int lb) {
+#define NAPA_PIPE_CASE(a, b)                                                    \
+    if (la == a && lb == b)                                                     \
+        return pk == 0 ? napa::fft_pipeline_kernel<a, b, 0> : (pk == 1 ? napa::fft_pipeline_kernel<a, b, 1> : napa::fft_pipeline_kernel<a, b, 2>);
+static pipe_fn pipe_kernel(int la, int lb, int pk) {
     NAPA_PIPE_CASE(7, 7) NAPA_PIPE_CASE(7, 8) NAPA_PIPE_CASE(8, 7) NAPA_PIPE_CASE(8, 8)
-#if NAPA_SMALL_TILE_MAXL != 8
-    NAPA_PIPE_CASE(8, 9) NAPA_PIPE_CASE(9, 8)
-#endif
     NAPA_PIPE_CASE(9, 9) NAPA_PIPE_CASE(9, 10)
     NAPA_PIPE_CASE(10, 9) NAPA_PIPE_CASE(10, 10) NAPA_PIPE_CASE(10, 11) NAPA_PIPE_CASE(11, 10)
     NAPA_PIPE_CASE(10, 12) NAPA_PIPE_CASE(12, 10)
@@ -274,14 +273,14 @@ static int ensure_counters(cudaStream_t st, size_t bytes, unsigned char **out) {
     return NAPA_OK;
 }
 
-static int launch_pipeline(int la, int lb, napa::PipeParams &pp, cudaStream_t st) {
-    pipe_fn fn = pipe_kernel(la, lb);
+static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStream_t st) {
+    pipe_fn fn = pipe_kernel(la, lb, pk);
     if (!fn) return fail(NAPA_E_UNSUPPORTED, "no pipeline kernel for digits (%d, %d)", la, lb);
     OK(ensure_stage_tw(la));
     OK(ensure_stage_tw(lb));
     pp.a.stage_tw = G.stage_tw[la];
     pp.b.stage_tw = G.stage_tw[lb];
-    const size_t smem = std::max(napa::plan_smem_bytes(la), napa::plan_smem_bytes(lb));
+    const size_t smem = std::max(napa::kind_smem_bytes(la, napa::pipe_kind_a(pk)), napa::kind_smem_bytes(lb, napa::pipe_kind_b(pk)));
     static std::map<pipe_fn, int> occupancy;
     auto it = occupancy.find(fn);
     if (it == occupancy.end()) {
@@ -411,7 +410,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         if (!inv && !o.in_order) pp.flags |= napa::PF_OUT_REV;
         first_pass_fusions(pp, o, n, win_rev);
         const long long C = 1LL << napa::plan_log2c(lg);
-        OK(launch_pass(lg, pp, ((long long)batch + C - 1) / C, st));
+        OK(launch_pass(lg, KIND_ROW, pp, ((long long)batch + C - 1) / C, st));
         CU(cudaGetLastError());
         return NAPA_OK;
     }
@@ -451,7 +450,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             pp.a_dst_is_ring = 1; pp.b_src_is_ring = 1;
             p1.src_hint = napa::HINT_STREAM; p1.dst_hint = napa::HINT_KEEP;
             p2.src_hint = napa::HINT_KEEP; p2.dst_hint = napa::HINT_STREAM;
-            OK(launch_pipeline(d[0], d[1], pp, st));
+            OK(launch_pipeline(d[0], d[1], 0, pp, st));
         } else {
             // bit-reversed layouts: in place on dst after the first pass, no scratch
             pp.slots = 0;
@@ -478,7 +477,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                 q.src_hint = step == 0 ? napa::HINT_STREAM : napa::HINT_KEEP;
                 q.dst_hint = step == 0 ? napa::HINT_KEEP : napa::HINT_STREAM;
             }
-            OK(launch_pipeline(d[order[0]], d[order[1]], pp, st));
+            OK(launch_pipeline(d[order[0]], d[order[1]], inv ? 2 : 1, pp, st));
         }
         CU(cudaGetLastError());
         return NAPA_OK;
@@ -498,7 +497,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << lg) - 1;
             first_pass_fusions(p1, o, n, win_rev);
             if (o.wpb) p1.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
-            OK(launch_pass(d[0], p1, tpi * (long long)nb, st));
+            OK(launch_pass(d[0], KIND_COL, p1, tpi * (long long)nb, st));
             PassParams p2{};
             pass_geometry(d, 1, p2, &tpi);
             p2.src = G.scratch; p2.dst = dst + b0 * dstride;
@@ -507,7 +506,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             // row k1 = ra*C + q, output k2 -> address k1 + L1*k2
             p2.d_SA = 1LL << napa::plan_log2c(d[1]); p2.d_SG = 0; p2.d_i = L1; p2.d_q = 1;
             (void)L2;
-            OK(launch_pass(d[1], p2, tpi * (long long)nb, st));
+            OK(launch_pass(d[1], KIND_ROWT, p2, tpi * (long long)nb, st));
         }
         CU(cudaGetLastError());
         return NAPA_OK;
@@ -545,7 +544,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                 first_pass_fusions(pp, oo, n, false);
                 if (o.wpb && o.wtype) pp.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
             }
-            OK(launch_pass(d[s], pp, tpi * (long long)nb, st));
+            OK(launch_pass(d[s], lgB > 0 ? KIND_COL : KIND_ROW, pp, tpi * (long long)nb, st));
         }
     }
     if (natural && !inv) OK(exec_bitrev(dst, dst, n, batch, dstride, dstride, NAPA_ELT_COMPLEX, st));
@@ -807,8 +806,6 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
     if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
-    if (const char *env = getenv("NAPAFFT_PERSIST")) G.use_persist = atoi(env) != 0;
-    if (const char *env = getenv("NAPAFFT_PF_WAVES")) G.pf_dist_waves = atoi(env);
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;

@@ -249,13 +249,55 @@ __device__ __forceinline__ long long rev_bits64(long long x, int w) {
     return w ? (long long)(__brevll((unsigned long long)x) >> (64 - w)) : 0;
 }
 
-// shared-memory slot of (position, interleaved transform q); see tools/bank_check.py
-template <int LOG2L>
-__device__ __forceinline__ int smem_phys(int pos, int q) {
-    return ((pos + (pos >> plan_padshift(LOG2L))) << plan_log2c(LOG2L)) + q;
+// ------------------------------------------------------------------------------------------
+// Lane maps and shared-memory layouts (validated by tools/bank_check.py)
+//   MAP_Q: transform index q fastest across lanes  -> a quarter warp covers 8 adjacent COLUMNS
+//          (one 128-byte segment of a column-like tile)
+//   MAP_T: position t fastest across lanes         -> a quarter warp covers 8 adjacent elements
+//          of one ROW (row-like tiles, single-pass transforms)
+// A 128-bit access costs one LSU data-pipe wavefront per distinct 128-byte line per quarter warp,
+// so the map must follow the contiguous direction of each side of the tile in global memory; the
+// map can change from the load side to the store side at the first shared-memory exchange.
+// Layouts: interleaved [pos][q] when both sides are MAP_Q, else planar [q][pos] with a pitch that
+// keeps both maps conflict-free.
+// ------------------------------------------------------------------------------------------
+enum { MAP_Q = 0, MAP_T = 1 };
+
+template <int LOG2L, int MAP>
+__device__ __forceinline__ void lane_ids(const int tid, int &t, int &q) {
+    if constexpr (MAP == MAP_Q) {
+        constexpr int LOG2C = plan_log2c(LOG2L);
+        q = tid & ((1 << LOG2C) - 1);
+        t = tid >> LOG2C;
+    } else {
+        constexpr int LOG2T = LOG2L - 4;
+        t = tid & ((1 << LOG2T) - 1);
+        q = tid >> LOG2T;
+    }
 }
 
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
+__host__ __device__ constexpr int planar_padshift(int l) { return plan_log2radix(l, 0); }
+__host__ __device__ constexpr int planar_pitch(int l) {
+    const int lc = plan_log2c(l);
+    const int skew = lc >= 3 ? 1 : (lc == 2 ? 2 : (lc == 1 ? 4 : 0));
+    return (1 << l) + ((1 << l) >> planar_padshift(l)) + skew;
+}
+__host__ __device__ constexpr size_t plan_smem_bytes_planar(int l) {
+    return plan_nstages(l) == 1 ? 0 : (size_t)(planar_pitch(l) << plan_log2c(l)) * sizeof(cplx);
+}
+
+template <int LOG2L, bool PLANAR>
+__device__ __forceinline__ int smem_phys(int pos, int q) {
+    if constexpr (PLANAR) return q * planar_pitch(LOG2L) + pos + (pos >> planar_padshift(LOG2L));
+    else return ((pos + (pos >> plan_padshift(LOG2L))) << plan_log2c(LOG2L)) + q;
+}
+// reorder buffer for bit-reversed row-side accesses: planar, low 3 position bits XOR reversed top 3
+template <int LOG2L>
+__device__ __forceinline__ int reorder_phys(int pos, int q) {
+    const int top = pos >> (LOG2L - 3);
+    const int r3 = ((top & 1) << 2) | (top & 2) | (top >> 2);
+    return (q << LOG2L) + (pos ^ r3);
+}
 
 // v[u + s*NB] *= w^s for s = 1 .. R-1
 template <int R, int NB>
@@ -287,10 +329,10 @@ __device__ __forceinline__ void twiddle_powers(cplx (&v)[16], const int u, const
     }
 }
 
-// PRESYNC0: the tile's input was staged in sm (thread-private slots); everyone must have read its
-// staged input before stage 0 scatters.  `hook` runs right after the gather of the LAST stage, i.e.
-// at the first moment sm is free again (used to issue the next tile's cp.async prefetch).
-template <int LOG2L, int STAGE, int LOG2NS, bool PRESYNC0, class Hook>
+// Stockham autosort stages.  Stage 0 runs under the load-side ids (t0, q0) and scatters; every
+// later stage gathers and runs under the store-side ids (t1, q1).  PRESYNC0: sm was used before
+// stage 0 (reorder of a bit-reversed load) and everyone must be done with it before the scatter.
+template <int LOG2L, int STAGE, int LOG2NS, bool PLANAR, bool PRESYNC0>
 struct Stages {
     static constexpr int L = 1 << LOG2L;
     static constexpr int T = L / 16;
@@ -300,12 +342,13 @@ struct Stages {
     static constexpr int NB = 16 / R;
     static constexpr int NS = 1 << LOG2NS;
 
-    static __device__ __forceinline__ void run(cplx (&v)[16], cplx *sm, const cplx *__restrict__ tw, int t, int q, Hook &hook) {
+    static __device__ __forceinline__ void run(cplx (&v)[16], cplx *sm, const cplx *__restrict__ tw,
+                                               const int t0, const int q0, const int t1, const int q1) {
+        const int t = STAGE == 0 ? t0 : t1, q = STAGE == 0 ? q0 : q1;
         if constexpr (STAGE > 0) {
             // exchange: previous stage wrote its scattered outputs; gather t + m*T
 #pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L>(t + m * T, q)];
-            if constexpr (STAGE + 1 == NSTAGES) hook();
+            for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L, PLANAR>(t + m * T, q)];
             // twiddle W_{NS*R}^{(jb % NS) * s} on input s of butterfly jb = t + u*T.  Only the seed
             // w = W^{jb % NS} is loaded; its powers come from a product tree (depth <= 4): the
             // LSU<->register datapath, not the FP64 pipe, is the scarce resource of this kernel.
@@ -332,10 +375,10 @@ struct Stages {
                 int jb = t + u * T;
                 int base = ((jb >> LOG2NS) << (LOG2NS + LOG2R)) + (jb & (NS - 1));
 #pragma unroll
-                for (int s = 0; s < R; s++) sm[smem_phys<LOG2L>(base + s * NS, q)] = v[u + s * NB];
+                for (int s = 0; s < R; s++) sm[smem_phys<LOG2L, PLANAR>(base + s * NS, q)] = v[u + s * NB];
             }
             __syncthreads();
-            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PRESYNC0, Hook>::run(v, sm, tw, t, q, hook);
+            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PLANAR, PRESYNC0>::run(v, sm, tw, t0, q0, t1, q1);
         }
     }
 };
@@ -362,7 +405,8 @@ __device__ __forceinline__ void apply_big_twiddle(cplx (&v)[16], const PassParam
     }
 }
 
-// Where a thread's 16 points of a tile live.  `tile` counts tiles over the whole launch (item-major).
+// Where a thread's 16 points of a tile live on one side.  `tile` counts tiles over the whole
+// launch (item-major).
 struct TileCtx {
     int q, t;
     long long item;
@@ -370,14 +414,11 @@ struct TileCtx {
     long long s_xoff, d_xoff;
     unsigned col;                    // column offset inside the [L][B] sub-matrix (twiddle exponent)
 };
-template <int LOG2L>
+template <int LOG2L, int MAP>
 __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long tile) {
-    constexpr int LOG2C = plan_log2c(LOG2L);
-    constexpr int C = 1 << LOG2C;
+    constexpr int C = 1 << plan_log2c(LOG2L);
     TileCtx c;
-    const int tid = threadIdx.x;
-    c.q = tid & (C - 1);
-    c.t = tid >> LOG2C;
+    lane_ids<LOG2L, MAP>(threadIdx.x, c.t, c.q);
     const long long b = tile / p.tiles_per_item;
     const int r = (int)(tile - b * p.tiles_per_item);
     const int ra = r / p.G, rg = r - ra * p.G;
@@ -395,75 +436,37 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
     return c;
 }
 
-// Asynchronously copy this thread's 16 input points of `tile` into its own shared-memory slots
-// (cp.async.cg: L2-coherent, no register staging).  The same thread gathers them later, so the
-// only synchronisation needed is cp.async.wait_group by that thread.
-template <int LOG2L>
-__device__ __forceinline__ void tile_prefetch(const PassParams &p, const long long tile, cplx *sm, const long long src_item_delta,
-                                              const L2Policies &pol) {
-    constexpr int T = (1 << LOG2L) / 16;
-    const TileCtx c = tile_ctx<LOG2L>(p, tile);
-    if (c.valid) {
-        const cplx *src = p.src + (c.item + src_item_delta) * p.src_batch_stride + c.s_xoff;
-        const long long s_i = p.s_i;
-        const int hint = p.src_hint;
-        if (p.flags & PF_IN_REV) {
-#pragma unroll
-            for (int m = 0; m < 16; m++)
-                cp_async16(sm + smem_phys<LOG2L>(c.t + m * T, c.q), src + (long long)rev_bits(c.t + m * T, LOG2L) * s_i, hint, pol);
-        } else {
-#pragma unroll
-            for (int m = 0; m < 16; m++)
-                cp_async16(sm + smem_phys<LOG2L>(c.t + m * T, c.q), src + (long long)(c.t + m * T) * s_i, hint, pol);
-        }
-    }
-    cp_async_commit();
-}
-
-// Software L2 prefetch of a whole tile: one prefetch.global.L2 per 128-byte line (issued by the
-// thread that owns the line's first element).  It costs no registers and no shared memory, so it
-// adds bytes in flight beyond what register-staged loads can hold (memory-level parallelism is
-// what bounds the HBM-facing pass).
-template <int LOG2L>
-__device__ __forceinline__ void tile_l2_prefetch(const PassParams &p, const long long tile) {
-    constexpr int T = (1 << LOG2L) / 16;
-    const TileCtx c = tile_ctx<LOG2L>(p, tile);
-    if (!c.valid) return;
-    const cplx *src = p.src + c.item * p.src_batch_stride + c.s_xoff;
-    const long long s_i = p.s_i;
-    const bool rev = (p.flags & PF_IN_REV) != 0;
-#pragma unroll
-    for (int m = 0; m < 16; m++) {
-        const cplx *a = src + (long long)(rev ? rev_bits(c.t + m * T, LOG2L) : c.t + m * T) * s_i;
-        if ((reinterpret_cast<unsigned long long>(a) & 127ull) == 0) l2_prefetch(a);
-    }
-}
-
-// One tile of one digit pass.  COHERENT selects L2-only (ld.global.cg) data loads: required when
-// the data was written earlier in the SAME launch by another SM (persistent pipeline), where a
-// stale L1 line would be a bug.  STAGED: the input was prefetched into sm by tile_prefetch.
-//
-// Structure matters for memory-level parallelism: all 16 data loads of a thread are issued
-// back to back into v[], and every optional fusion is a separate warp-uniform branch over the
-// whole register array (not a predicated snippet per element), so that unused fusions cost
-// nothing and used ones do not serialise the loads.
-template <int LOG2L, bool COHERENT, bool STAGED, class Hook>
+// One tile of one digit pass.
+//   COHERENT: L2-only (ld.global.cg) data loads, required when another SM wrote the data earlier
+//             in the SAME launch (persistent pipeline): a stale L1 line would be a bug.
+//   LM / SM_: lane maps of the load side and of the store side.
+// All 16 data loads of a thread are issued back to back into v[], and every optional fusion is a
+// separate warp-uniform branch over the whole register array, so unused fusions cost nothing and
+// used ones do not serialise the loads.
+template <int LOG2L, bool COHERENT, int LM, int SM_>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
-                                         const long long src_item_delta, const long long dst_item_delta, Hook &hook,
+                                         const long long src_item_delta, const long long dst_item_delta,
                                          const L2Policies &pol) {
     constexpr int L = 1 << LOG2L;
     constexpr int T = L / 16;
-    static_assert(!STAGED || plan_nstages(LOG2L) > 1, "staging needs a shared-memory buffer");
+    constexpr bool PLANAR = !(LM == MAP_Q && SM_ == MAP_Q);
+    constexpr bool REORDER_OK = LOG2L >= 7 && plan_nstages(LOG2L) > 1;   // swizzled reorder buffer
+    static_assert(plan_nstages(LOG2L) > 1 || LM == SM_, "single-stage tiles cannot switch lane maps");
     const int src_hint = p.src_hint, dst_hint = p.dst_hint;
-    const TileCtx c = tile_ctx<LOG2L>(p, tile);
-    const int t = c.t, q = c.q;
     const unsigned flags = p.flags;
+    const TileCtx c = tile_ctx<LOG2L, LM>(p, tile);
+    const int t = c.t, q = c.q;
     const long long s_xoff = c.s_xoff;
+    // a bit-reversed access on a row side goes through shared memory so that global memory sees
+    // whole contiguous lines; on a column side only the row index is permuted (free)
+    const bool in_reorder = REORDER_OK && LM == MAP_T && (flags & PF_IN_REV);
 
     cplx v[16];
     if (c.valid) {
         const cplx *src = p.src + (c.item + src_item_delta) * p.src_batch_stride + s_xoff;
         const long long s_i = p.s_i;
+        // memory position of register m on the load side
+        auto lpos = [&](int m) -> int { return ((flags & PF_IN_REV) && !in_reorder) ? rev_bits(t + m * T, LOG2L) : t + m * T; };
         // real window values are fetched first: they do not depend on the data and their L2
         // latency then overlaps the data wait
         double wv[16];
@@ -471,26 +474,17 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             const double *w = reinterpret_cast<const double *>(p.window) + c.item * p.window_batch_stride;
 #pragma unroll
             for (int m = 0; m < 16; m++) {
-                const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + m * T, LOG2L) : t + m * T) * s_i;
+                const long long off = s_xoff + (long long)lpos(m) * s_i;
                 wv[m] = __ldg(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
             }
         }
-        if (STAGED) {
-            cp_async_wait_all();
 #pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L>(t + m * T, q)];
-        } else if (flags & PF_IN_REV) {
-#pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i, src_hint, pol);
-        } else {
-#pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)(t + m * T) * s_i, src_hint, pol);
-        }
+        for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)lpos(m) * s_i, src_hint, pol);
         if (flags & PF_RIFFT_PRE) {
             // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177)
 #pragma unroll
             for (int m = 0; m < 16; m++) {
-                const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + m * T, LOG2L) : t + m * T) * s_i;
+                const long long off = s_xoff + (long long)lpos(m) * s_i;
                 const cplx y = ld_data<COHERENT>(src - s_xoff + off + p.aux_off, src_hint, pol);
                 const cplx w = ldg_c(p.r2tw + off);
                 v[m] = cadd(cadd(v[m], y), cmul(csub(v[m], y), w));
@@ -512,8 +506,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
                 cplx wc[8];
 #pragma unroll
                 for (int m = 0; m < 8; m++) {
-                    const int mm = 8 * h + m;
-                    const long long off = s_xoff + (long long)((flags & PF_IN_REV) ? rev_bits(t + mm * T, LOG2L) : t + mm * T) * s_i;
+                    const long long off = s_xoff + (long long)lpos(8 * h + m) * s_i;
                     wc[m] = ldg_c(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
                 }
 #pragma unroll
@@ -524,62 +517,93 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
         }
-        if (flags & PF_TW_LOAD) apply_big_twiddle<T>(v, p, t, c.col);
     } else {
-        if (STAGED) cp_async_wait_all();
 #pragma unroll
         for (int m = 0; m < 16; m++) v[m] = make_double2(0.0, 0.0);
     }
+    if constexpr (REORDER_OK && LM == MAP_T) {
+        if (in_reorder) {
+            // registers hold memory positions t + m*T; fetch logical input k = t + m*T from rev(k)
+#pragma unroll
+            for (int m = 0; m < 16; m++) sm[reorder_phys<LOG2L>(t + m * T, q)] = v[m];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = sm[reorder_phys<LOG2L>(rev_bits(t + m * T, LOG2L), q)];
+        }
+    }
+    if (c.valid && (flags & PF_TW_LOAD)) apply_big_twiddle<T>(v, p, t, c.col);
 
-    Stages<LOG2L, 0, 0, STAGED, Hook>::run(v, sm, p.stage_tw, t, q, hook);
+    const TileCtx d = tile_ctx<LOG2L, SM_>(p, tile);
+    if constexpr (REORDER_OK && LM == MAP_T) {
+        if (in_reorder) Stages<LOG2L, 0, 0, PLANAR, true>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+        else Stages<LOG2L, 0, 0, PLANAR, false>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+    } else {
+        Stages<LOG2L, 0, 0, PLANAR, false>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+    }
 
-    if (c.valid) {
-        if (flags & PF_TW_STORE) apply_big_twiddle<T>(v, p, t, c.col);
+    const bool out_reorder = REORDER_OK && SM_ == MAP_T && (flags & PF_OUT_REV);
+    if (d.valid) {
+        if (flags & PF_TW_STORE) apply_big_twiddle<T>(v, p, d.t, d.col);
         if (flags & PF_CONJ_OUT) {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
         }
-        cplx *dst = p.dst + (c.item + dst_item_delta) * p.dst_batch_stride + c.d_xoff;
-        const long long d_i = p.d_i;
-        if (flags & PF_OUT_REV) {
+    }
+    if constexpr (REORDER_OK && SM_ == MAP_T) {
+        if (out_reorder) {
+            // registers hold outputs k = t + m*T; move the value of memory position t + m*T here
+            __syncthreads();                   // everyone is done gathering the last exchange
 #pragma unroll
-            for (int m = 0; m < 16; m++) st_data(dst + (long long)rev_bits(t + m * T, LOG2L) * d_i, v[m], dst_hint, pol);
+            for (int m = 0; m < 16; m++) sm[reorder_phys<LOG2L>(rev_bits(d.t + m * T, LOG2L), d.q)] = v[m];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = sm[reorder_phys<LOG2L>(d.t + m * T, d.q)];
+        }
+    }
+    if (d.valid) {
+        cplx *dst = p.dst + (d.item + dst_item_delta) * p.dst_batch_stride + d.d_xoff;
+        const long long d_i = p.d_i;
+        if ((flags & PF_OUT_REV) && !out_reorder) {
+#pragma unroll
+            for (int m = 0; m < 16; m++) st_data(dst + (long long)rev_bits(d.t + m * T, LOG2L) * d_i, v[m], dst_hint, pol);
         } else {
 #pragma unroll
-            for (int m = 0; m < 16; m++) st_data(dst + (long long)(t + m * T) * d_i, v[m], dst_hint, pol);
+            for (int m = 0; m < 16; m++) st_data(dst + (long long)(d.t + m * T) * d_i, v[m], dst_hint, pol);
         }
     }
 }
 
-// Single-pass transforms (n <= 2^13).  Small launches: one tile per CTA, loads straight to
-// registers.  Large launches (persist != 0): persistent CTAs walk tiles blockIdx.x, +gridDim.x, ...
-// and prefetch the next tile with cp.async while the last radix stage of the current one runs.
-template <int LOG2L>
+// Software L2 prefetch of a whole tile (one prefetch.global.L2 per 128-byte line).  Measured
+// neutral on B200 for this kernel (the limit was the LSU data pipe, not DRAM-side MLP); kept
+// for the debug knob only.
+template <int LOG2L, int LM>
+__device__ __forceinline__ void tile_l2_prefetch(const PassParams &p, const long long tile) {
+    constexpr int T = (1 << LOG2L) / 16;
+    const TileCtx c = tile_ctx<LOG2L, LM>(p, tile);
+    if (!c.valid) return;
+    const cplx *src = p.src + c.item * p.src_batch_stride + c.s_xoff;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const cplx *a = src + (long long)(c.t + m * T) * p.s_i;
+        if ((reinterpret_cast<unsigned long long>(a) & 127ull) == 0) l2_prefetch(a);
+    }
+}
+
+// Lane maps by tile kind: 0 = column-like (Q,Q); 1 = row-like (T,T); 2 = row-like load,
+// column-like (transposed) store (T,Q).  L < 128 always uses (Q,Q).
+__host__ __device__ constexpr int kind_lm(int l, int kind) { return l >= 7 && kind != 0 ? MAP_T : MAP_Q; }
+__host__ __device__ constexpr int kind_sm(int l, int kind) { return l >= 7 && kind == 1 ? MAP_T : MAP_Q; }
+__host__ __device__ constexpr size_t kind_smem_bytes(int l, int kind) {
+    return (kind_lm(l, kind) == MAP_Q && kind_sm(l, kind) == MAP_Q) ? plan_smem_bytes(l) : plan_smem_bytes_planar(l);
+}
+
+// One tile per CTA (single-pass transforms, and the multi-launch fallback of multi-pass ones).
+template <int LOG2L, int KIND>
 __global__ void __launch_bounds__(plan_threads(LOG2L), plan_min_ctas(LOG2L))
-fft_pass_kernel(const PassParams p, const long long ntiles, const int persist, const int pf_dist) {
+fft_pass_kernel(const PassParams p) {
     NAPA_DYN_SMEM(cplx, sm);
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
-    if (pf_dist > 0 && (long long)blockIdx.x + pf_dist < ntiles) tile_l2_prefetch<LOG2L>(p, (long long)blockIdx.x + pf_dist);
-    if constexpr (plan_nstages(LOG2L) > 1) {
-        if (persist) {
-            long long tile = blockIdx.x;
-            if (tile >= ntiles) return;
-            tile_prefetch<LOG2L>(p, tile, sm, 0, pol);
-            for (;;) {
-                const long long next = tile + gridDim.x;
-                auto hook = [&]() {
-                    __syncthreads();                       // sm is free: everyone gathered the last exchange
-                    if (next < ntiles) tile_prefetch<LOG2L>(p, next, sm, 0, pol);
-                };
-                run_tile<LOG2L, false, true>(p, tile, sm, 0, 0, hook, pol);
-                if (next >= ntiles) break;
-                tile = next;
-            }
-            return;
-        }
-    }
-    NoHook nh;
-    run_tile<LOG2L, false, false>(p, (long long)blockIdx.x, sm, 0, 0, nh, pol);
+    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND)>(p, (long long)blockIdx.x, sm, 0, 0, pol);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -591,9 +615,8 @@ fft_pass_kernel(const PassParams p, const long long ntiles, const int persist, c
 // spin by one thread) until done[A][c] == tiles(c); deadlock-free because a waiter only ever
 // waits on lower tickets, which are held by running CTAs.  With a scratch ring (natural-order
 // output) pass A of chunk c additionally waits for pass B of chunk c - SLOTS to have drained
-// the slot it is about to overwrite.
-// The loop is software-pipelined: while the last radix stage of tile k runs, the input of tile
-// k+1 (already ticketed, dependencies checked without blocking) is in flight via cp.async.
+// the slot it is about to overwrite.  Tickets are decoded two tiles ahead by one thread so that
+// the atomic, the decode and the dependency check stay off the critical path.
 // ------------------------------------------------------------------------------------------
 struct PipeParams {
     PassParams a, b;                 // pass A (first executed) and pass B
@@ -603,11 +626,11 @@ struct PipeParams {
     int lag;                         // phases between pass A and pass B of a chunk
     int slots;                       // scratch ring slots (0: intermediate lives in dst)
     int a_dst_is_ring, b_src_is_ring;
-    long long tiles_per_item;        // same for both passes (C*L = 4096)
+    long long tiles_per_item;        // same for both passes (same tile shape)
     unsigned long long *ticket;      // zeroed before launch
     unsigned *done;                  // [2][nchunks], zeroed before launch
     int *error;                      // set to 1 if a wait timed out (never expected)
-    int debug;                       // bit0: no hook prefetch
+    int debug;
 };
 
 __device__ __forceinline__ long long pipe_tilesum(const PipeParams &p, long long k) {
@@ -675,15 +698,16 @@ __device__ __forceinline__ void pipe_wait(const PipeWork &w, int *error) {
     __threadfence();
 }
 
-template <int LA, int LB>
-__device__ __forceinline__ void pipe_prefetch(const PipeParams &p, const PipeWork &w, cplx *sm, const L2Policies &pol) {
-    if (w.is_a) tile_prefetch<LA>(p.a, w.tile, sm, 0, pol);
-    else tile_prefetch<LB>(p.b, w.tile, sm, p.b_src_is_ring ? w.delta : 0, pol);
-}
+// PK: 0 = natural order   (A column-like (Q,Q) into the ring, B row-like load + transposed store (T,Q))
+//     1 = forward, bit-reversed output (A column-like, B row-like (T,T))
+//     2 = inverse, bit-reversed input  (A row-like (T,T), B column-like)
+__host__ __device__ constexpr int pipe_kind_a(int pk) { return pk == 2 ? 1 : 0; }
+__host__ __device__ constexpr int pipe_kind_b(int pk) { return pk == 0 ? 2 : (pk == 1 ? 1 : 0); }
 
-template <int LA, int LB>
+template <int LA, int LB, int PK>
 __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
+    constexpr int KA = pipe_kind_a(PK), KB = pipe_kind_b(PK);
     NAPA_DYN_SMEM(cplx, sm);
     __shared__ PipeWork s_work[3];                   // ring: current tile, next tile, the one being decoded
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
@@ -706,8 +730,7 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipel
         const PipeWork cur = s_work[k % 3];
         if (cur.tile < 0) break;
         const PipeWork nxt = s_work[(k + 1) % 3];
-        // the HBM-facing pass (A reads the caller's src) gets its next tile pulled into L2 now
-        if (nxt.tile >= 0 && nxt.is_a && !(p.debug & 4)) tile_l2_prefetch<LA>(p.a, nxt.tile);
+        if ((p.debug & 4) && nxt.tile >= 0 && nxt.is_a) tile_l2_prefetch<LA, kind_lm(LA, KA)>(p.a, nxt.tile);
         if (threadIdx.x == 0) {
             PipeWork w;
             w.tile = -1;
@@ -717,9 +740,8 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipel
             }
             s_work[(k + 2) % 3] = w;
         }
-        NoHook hook;
-        if (cur.is_a) run_tile<LA, true, false>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, hook, pol);
-        else run_tile<LB, true, false>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, hook, pol);
+        if (cur.is_a) run_tile<LA, true, kind_lm(LA, KA), kind_sm(LA, KA)>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, pol);
+        else run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB)>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, pol);
         __syncthreads();                       // all stores of this tile issued
         if (threadIdx.x == 0) {
             __threadfence();

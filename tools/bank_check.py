@@ -1,58 +1,125 @@
 """Static shared-memory bank-conflict check of the exchange patterns in
-napa_fft3_b200/csrc/napafft_kernels.cuh (Stages<>::run): for every tile shape it replays the
-addresses each warp instruction touches and counts 128-byte wavefronts (a quarter warp of 16-byte
-accesses is conflict-free iff its 8 addresses fall in 8 distinct 16-byte bank groups).
-Run: python tools/bank_check.py"""
+napa_fft3_b200/csrc/napafft_kernels.cuh: for every tile shape, lane mapping (Q = transform index
+fastest across lanes, T = position fastest) and layout (interleaved [pos][q] / planar [q][pos])
+it replays the 16-byte addresses of every warp instruction and counts 128-byte wavefronts
+(a quarter warp is conflict-free iff its 8 addresses fall in 8 distinct 16-byte bank groups).
+Run: python tools/bank_check.py      (exits non-zero on any conflict)"""
+import sys
+
 PLANS = {4: [4], 5: [3, 2], 6: [3, 3], 7: [4, 3], 8: [4, 4], 9: [3, 3, 3], 10: [4, 4, 2], 11: [4, 4, 3],
          12: [4, 4, 4], 13: [4, 4, 3, 2]}
+SMALL_TILE_MAXL = 8
+
+
+def log2pts(l):
+    return 11 if l <= SMALL_TILE_MAXL else (12 if l <= 12 else 13)
 
 
 def wavefronts(addrs16):
-    """addrs16: 32 lane addresses in 16-byte units -> number of 128 B wavefronts for an LDS/STS.128"""
     total = 0
-    for qw in range(4):
-        lanes = addrs16[8 * qw: 8 * qw + 8]
+    for qw in range(0, len(addrs16), 8):
         groups = {}
-        for a in lanes:
+        for a in addrs16[qw:qw + 8]:
             groups.setdefault(a % 8, set()).add(a)
         total += max(len(v) for v in groups.values())
     return total
 
 
-def check(l, padshift=None):
-    L = 1 << l
-    T = L // 16
-    lc = 12 - l if l <= 12 else 0
-    C = 1 << lc
-    if padshift is None:
-        padshift = 31 if lc >= 3 else 4
-    nthreads = T * C
-    phys = lambda pos, q: ((pos + (pos >> padshift)) << lc) + q
-    worst_r = worst_w = 4
+def ids(tid, l, m):
+    lc = log2pts(l) - l
+    lt = l - 4
+    if m == "Q":
+        return tid >> lc, tid & ((1 << lc) - 1)          # t, q
+    return tid & ((1 << lt) - 1), tid >> lt
+
+
+def planar_params(l):
+    lc = log2pts(l) - l
+    T = 1 << (l - 4)
+    padsh = PLANS[l][0]
+    if T >= 8:
+        skew = 1 if lc >= 3 else (2 if lc == 2 else (4 if lc == 1 else 0))
+    else:
+        skew = 8 // T if T > 1 else 0
+    return padsh, (1 << l) + ((1 << l) >> padsh) + skew
+
+
+def phys(l, layout, pos, q):
+    lc = log2pts(l) - l
+    if layout == "I":
+        padsh = 31 if lc >= 3 else 4
+        return ((pos + (pos >> padsh)) << lc) + q
+    padsh, pitch = planar_params(l)
+    return q * pitch + pos + (pos >> padsh)
+
+
+def rphys(l, pos, q):
+    """reorder buffer: planar, XOR swizzle of the low 3 bits with the reversed top 3 bits"""
+    top = pos >> (l - 3)
+    r3 = ((top & 1) << 2) | (top & 2) | (top >> 2)
+    return q * (1 << l) + (pos ^ r3)
+
+
+def rev(x, w):
+    return int(format(x, "0%db" % w)[::-1], 2) if w else 0
+
+
+def check(l, lm, sm):
+    L, T = 1 << l, 1 << (l - 4)
+    nthreads = 1 << (log2pts(l) - 4)
+    layout = "I" if (lm == "Q" and sm == "Q") else "P"
+    worst_w = worst_r = 4
     lgns = 0
     radices = PLANS[l]
     for st, lr in enumerate(radices[:-1]):
         R, NB, NS = 1 << lr, 16 >> lr, 1 << lgns
+        wm = lm if st == 0 else sm
         for w0 in range(0, nthreads, 32):
-            tids = range(w0, w0 + 32)
+            tids = range(w0, min(w0 + 32, nthreads))
             for u in range(NB):
                 for s in range(R):
                     addrs = []
                     for tid in tids:
-                        q, t = tid & (C - 1), tid >> lc
+                        t, q = ids(tid, l, wm)
                         jb = t + u * T
                         base = ((jb >> lgns) << (lgns + lr)) + (jb & (NS - 1))
-                        addrs.append(phys(base + s * NS, q))
-                    worst_w = max(worst_w, wavefronts(addrs))
+                        addrs.append(phys(l, layout, base + s * NS, q))
+                    worst_w = max(worst_w, wavefronts(addrs) * 32 // len(addrs))
             for m in range(16):
-                addrs = [phys((tid >> lc) + m * T, tid & (C - 1)) for tid in tids]
-                worst_r = max(worst_r, wavefronts(addrs))
+                addrs = []
+                for tid in tids:
+                    t, q = ids(tid, l, sm)
+                    addrs.append(phys(l, layout, t + m * T, q))
+                worst_r = max(worst_r, wavefronts(addrs) * 32 // len(addrs))
         lgns += lr
     return worst_w, worst_r
 
 
+def check_reorder(l):
+    T = 1 << (l - 4)
+    nthreads = 1 << (log2pts(l) - 4)
+    worst = 4
+    for w0 in range(0, nthreads, 32):
+        tids = range(w0, min(w0 + 32, nthreads))
+        for m in range(16):
+            nat = [rphys(l, ids(tid, l, "T")[0] + m * T, ids(tid, l, "T")[1]) for tid in tids]
+            rv = [rphys(l, rev(ids(tid, l, "T")[0] + m * T, l), ids(tid, l, "T")[1]) for tid in tids]
+            worst = max(worst, wavefronts(nat), wavefronts(rv))
+    return worst
+
+
 if __name__ == "__main__":
+    bad = 0
     for l in range(5, 14):
-        w, r = check(l)
-        print("L=2^%-2d C=%-3d plan=%s  worst STS wavefronts/instr %d (ideal 4), LDS %d" % (
-            l, 1 << (12 - l if l <= 12 else 0), [1 << x for x in PLANS[l]], w, r))
+        for lm, sm in (("Q", "Q"), ("T", "T"), ("T", "Q")):
+            w, r = check(l, lm, sm)
+            flag = "" if (w, r) == (4, 4) else "   <-- CONFLICT"
+            bad += flag != ""
+            print("L=2^%-2d C=%-3d plan=%-16s load map %s store map %s: STS wavefronts/instr %d LDS %d (ideal 4)%s" % (
+                l, 1 << (log2pts(l) - l), [1 << x for x in PLANS[l]], lm, sm, w, r, flag))
+        if l >= 7:
+            w = check_reorder(l)
+            flag = "" if w == 4 else "   <-- CONFLICT"
+            bad += flag != ""
+            print("L=2^%-2d bit-reversal reorder buffer (T map, XOR swizzle): %d wavefronts/instr%s" % (l, w, flag))
+    sys.exit(1 if bad else 0)
