@@ -286,7 +286,7 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     if (it == occupancy.end()) {
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la), smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la) + 32, smem));
         if (nb < 1) return fail(NAPA_E_CUDA, "pipeline kernel does not fit on an SM");
         it = occupancy.emplace(fn, nb).first;
     }
@@ -301,7 +301,7 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
     const long long total_tiles = pp.items * pp.tiles_per_item * 2;
     long long grid = std::min<long long>((long long)G.num_sms * it->second, total_tiles);
-    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la), smem, st, pp);
+    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la) + 32, smem, st, pp);
     g_launches++;
     return NAPA_OK;
 }

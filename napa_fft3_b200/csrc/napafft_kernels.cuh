@@ -243,6 +243,18 @@ __device__ __forceinline__ void l2_prefetch(const void *g) { asm volatile("prefe
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #endif
+// CTA-wide barrier, or a named barrier over the NT compute threads of a kernel that also runs a
+// control warp (persistent pipeline)
+struct SyncAll { static __device__ __forceinline__ void sync() { __syncthreads(); } };
+#ifdef NAPA_EMULATE
+__device__ __forceinline__ void named_bar_sync(int id, int count) { napa_emul::bar_sync(id, (unsigned)count); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { napa_emul::bar_arrive(id, (unsigned)count); }
+#else
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+#endif
+template <int NT> struct SyncCompute { static __device__ __forceinline__ void sync() { named_bar_sync(1, NT); } };
+
 // rev_w(x): reverse the low w bits of x (w = 0 -> 0)
 __device__ __forceinline__ int rev_bits(int x, int w) { return w ? (int)(__brev((unsigned)x) >> (32 - w)) : 0; }
 __device__ __forceinline__ long long rev_bits64(long long x, int w) {
@@ -332,7 +344,7 @@ __device__ __forceinline__ void twiddle_powers(cplx (&v)[16], const int u, const
 // Stockham autosort stages.  Stage 0 runs under the load-side ids (t0, q0) and scatters; every
 // later stage gathers and runs under the store-side ids (t1, q1).  PRESYNC0: sm was used before
 // stage 0 (reorder of a bit-reversed load) and everyone must be done with it before the scatter.
-template <int LOG2L, int STAGE, int LOG2NS, bool PLANAR, bool PRESYNC0>
+template <int LOG2L, int STAGE, int LOG2NS, bool PLANAR, bool PRESYNC0, class Sync>
 struct Stages {
     static constexpr int L = 1 << LOG2L;
     static constexpr int T = L / 16;
@@ -369,7 +381,7 @@ struct Stages {
             for (int s = 0; s < R; s++) v[u + s * NB] = w[s];
         }
         if constexpr (STAGE + 1 < NSTAGES) {
-            if constexpr (STAGE > 0 || PRESYNC0) __syncthreads();   // everyone has gathered before we overwrite
+            if constexpr (STAGE > 0 || PRESYNC0) Sync::sync();   // everyone has gathered before we overwrite
 #pragma unroll
             for (int u = 0; u < NB; u++) {
                 int jb = t + u * T;
@@ -377,8 +389,8 @@ struct Stages {
 #pragma unroll
                 for (int s = 0; s < R; s++) sm[smem_phys<LOG2L, PLANAR>(base + s * NS, q)] = v[u + s * NB];
             }
-            __syncthreads();
-            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PLANAR, PRESYNC0>::run(v, sm, tw, t0, q0, t1, q1);
+            Sync::sync();
+            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PLANAR, PRESYNC0, Sync>::run(v, sm, tw, t0, q0, t1, q1);
         }
     }
 };
@@ -443,7 +455,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 // All 16 data loads of a thread are issued back to back into v[], and every optional fusion is a
 // separate warp-uniform branch over the whole register array, so unused fusions cost nothing and
 // used ones do not serialise the loads.
-template <int LOG2L, bool COHERENT, int LM, int SM_>
+template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync = SyncAll, bool REUSE = false>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
                                          const long long src_item_delta, const long long dst_item_delta,
                                          const L2Policies &pol) {
@@ -524,9 +536,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     if constexpr (REORDER_OK && LM == MAP_T) {
         if (in_reorder) {
             // registers hold memory positions t + m*T; fetch logical input k = t + m*T from rev(k)
+            if constexpr (REUSE) Sync::sync();   // previous tile may still be reading sm
 #pragma unroll
             for (int m = 0; m < 16; m++) sm[reorder_phys<LOG2L>(t + m * T, q)] = v[m];
-            __syncthreads();
+            Sync::sync();
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = sm[reorder_phys<LOG2L>(rev_bits(t + m * T, LOG2L), q)];
         }
@@ -535,10 +548,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 
     const TileCtx d = tile_ctx<LOG2L, SM_>(p, tile);
     if constexpr (REORDER_OK && LM == MAP_T) {
-        if (in_reorder) Stages<LOG2L, 0, 0, PLANAR, true>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
-        else Stages<LOG2L, 0, 0, PLANAR, false>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+        if (in_reorder) Stages<LOG2L, 0, 0, PLANAR, true, Sync>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+        else Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
     } else {
-        Stages<LOG2L, 0, 0, PLANAR, false>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+        Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
     }
 
     const bool out_reorder = REORDER_OK && SM_ == MAP_T && (flags & PF_OUT_REV);
@@ -552,10 +565,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     if constexpr (REORDER_OK && SM_ == MAP_T) {
         if (out_reorder) {
             // registers hold outputs k = t + m*T; move the value of memory position t + m*T here
-            __syncthreads();                   // everyone is done gathering the last exchange
+            Sync::sync();                      // everyone is done gathering the last exchange
 #pragma unroll
             for (int m = 0; m < 16; m++) sm[reorder_phys<LOG2L>(rev_bits(d.t + m * T, LOG2L), d.q)] = v[m];
-            __syncthreads();
+            Sync::sync();
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = sm[reorder_phys<LOG2L>(d.t + m * T, d.q)];
         }
@@ -704,50 +717,79 @@ __device__ __forceinline__ void pipe_wait(const PipeWork &w, int *error) {
 __host__ __device__ constexpr int pipe_kind_a(int pk) { return pk == 2 ? 1 : 0; }
 __host__ __device__ constexpr int pipe_kind_b(int pk) { return pk == 0 ? 2 : (pk == 1 ? 1 : 0); }
 
+// Threads [0, NT) are compute warps; one extra CONTROL warp draws and decodes tickets two tiles
+// ahead, waits for dependencies and publishes completion (fence + atomic) -- all off the compute
+// warps' critical path.  Named barriers: 1 = compute warps only (exchanges), 2 = top of tile
+// (everyone), 3 = "stores of this tile issued" (compute warps arrive, control warp waits).
 template <int LA, int LB, int PK>
-__global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
+__global__ void __launch_bounds__(plan_threads(LA) + 32, plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
     constexpr int KA = pipe_kind_a(PK), KB = pipe_kind_b(PK);
+    constexpr int NT = plan_threads(LA);
     NAPA_DYN_SMEM(cplx, sm);
-    __shared__ PipeWork s_work[3];                   // ring: current tile, next tile, the one being decoded
-    const L2Policies pol = make_policies();          // created once per thread, at kernel entry
+    __shared__ PipeWork s_work[3];                   // ring: slot k%3 = k-th tile of this CTA
     const long long nphase = (long long)p.nchunks + p.lag;
     const long long total = pipe_prefix(p, nphase);
-    long long next_ticket = 0;
-    if (threadIdx.x == 0) {
-        // tickets of this CTA are decoded two tiles ahead: slot k%3 = tile k
-        PipeWork w0 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
-        PipeWork w1 = w0;
-        w1.tile = -1;
-        if (w0.tile >= 0) w1 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
-        if (w1.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
-        if (w0.tile >= 0 && !w0.ready) pipe_wait(w0, p.error);
-        s_work[0] = w0;
-        s_work[1] = w1;
+    if (threadIdx.x >= NT) {
+        // ---------------- control warp ----------------
+        const bool lead = threadIdx.x == NT;
+        long long next_ticket = 0;
+        if (lead) {
+            PipeWork w0 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
+            PipeWork w1 = w0;
+            w1.tile = -1;
+            if (w0.tile >= 0) w1 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
+            if (w1.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+            if (w0.tile >= 0 && !w0.ready) pipe_wait(w0, p.error);
+            s_work[0] = w0;
+            s_work[1] = w1;
+        }
+        bool pending = false;                        // completion of the previous tile not yet published
+        unsigned *pending_ctr = nullptr;
+        for (int k = 0;; k++) {
+            named_bar_sync(2, NT + 32);              // top of tile k: slots k and k+1 are published
+            const bool stop = s_work[k % 3].tile < 0;   // written by the lead lane >= 1 barrier ago
+            if (lead) {
+                if (pending) { __threadfence(); atomicAdd(pending_ctr, 1u); pending = false; }   // overlaps tile k
+                if (!stop) {
+                    const PipeWork cur = s_work[k % 3];
+                    const PipeWork nxt = s_work[(k + 1) % 3];
+                    PipeWork w;
+                    w.tile = -1;
+                    if (nxt.tile >= 0) {
+                        w = pipe_decode(p, next_ticket, nphase, total);
+                        if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+                    }
+                    s_work[(k + 2) % 3] = w;
+                    pending_ctr = p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk;
+                }
+            }
+            if (stop) break;
+            named_bar_sync(3, NT + 32);              // compute warps have issued every store of tile k
+            if (lead) {
+                const PipeWork nxt = s_work[(k + 1) % 3];
+                const bool must_wait = nxt.tile >= 0 && nxt.dep && ld_acquire_u32(nxt.dep) < nxt.dep_target;
+                if (must_wait) {
+                    // the next tile may depend on this very tile: publish before blocking
+                    __threadfence(); atomicAdd(pending_ctr, 1u);
+                    pipe_wait(nxt, p.error);
+                } else {
+                    __threadfence();                 // acquire side of the non-blocking dependency check
+                    pending = true;
+                }
+            }
+        }
+        return;
     }
+    // ---------------- compute warps ----------------
+    const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     for (int k = 0;; k++) {
-        __syncthreads();                       // publishes slots k%3 and (k+1)%3; slot (k+2)%3 is free
+        named_bar_sync(2, NT + 32);
         const PipeWork cur = s_work[k % 3];
         if (cur.tile < 0) break;
-        const PipeWork nxt = s_work[(k + 1) % 3];
-        if ((p.debug & 4) && nxt.tile >= 0 && nxt.is_a) tile_l2_prefetch<LA, kind_lm(LA, KA)>(p.a, nxt.tile);
-        if (threadIdx.x == 0) {
-            PipeWork w;
-            w.tile = -1;
-            if (nxt.tile >= 0) {
-                w = pipe_decode(p, next_ticket, nphase, total);
-                if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);   // latency hidden behind this tile
-            }
-            s_work[(k + 2) % 3] = w;
-        }
-        if (cur.is_a) run_tile<LA, true, kind_lm(LA, KA), kind_sm(LA, KA)>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, pol);
-        else run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB)>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, pol);
-        __syncthreads();                       // all stores of this tile issued
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk, 1u);
-            if (nxt.tile >= 0 && !nxt.ready) pipe_wait(nxt, p.error);   // dependencies of the next tile (rarely late)
-        }
+        if (cur.is_a) run_tile<LA, true, kind_lm(LA, KA), kind_sm(LA, KA), SyncCompute<NT>, true>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, pol);
+        else run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncCompute<NT>, true>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, pol);
+        named_bar_arrive(3, NT + 32);
     }
 }
 

@@ -8,6 +8,7 @@ namespace napa_emul {
 uint3_ threadIdx_, blockIdx_;
 dim3 blockDim_, gridDim_;
 unsigned char *dyn_smem = nullptr;
+int shfl_slot[64];
 
 namespace {
 constexpr size_t kStack = 96 * 1024;
@@ -25,10 +26,30 @@ void trampoline() {
 }
 }  // namespace
 
-void syncthreads() {
+namespace {
+unsigned bar_arrived[16];
+unsigned long long bar_gen[16];
+unsigned long long progress = 0;
+}
+
+static void yield_fiber() {
     fibers[current].st = AT_BARRIER;
     swapcontext(&fibers[current].ctx, &sched_ctx);
 }
+
+void bar_arrive(int id, unsigned count) {
+    progress++;
+    if (++bar_arrived[id] >= count) { bar_arrived[id] = 0; bar_gen[id]++; }
+}
+
+void bar_sync(int id, unsigned count) {
+    progress++;
+    if (++bar_arrived[id] >= count) { bar_arrived[id] = 0; bar_gen[id]++; return; }
+    const unsigned long long g = bar_gen[id];
+    while (bar_gen[id] == g) yield_fiber();
+}
+
+void syncthreads() { bar_sync(0, blockDim_.x * blockDim_.y * blockDim_.z); }
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
     const unsigned nthreads = block.x * block.y * block.z;
@@ -55,8 +76,10 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
             makecontext(&f.ctx, trampoline, 0);
             f.st = READY;
         }
+        for (int i = 0; i < 16; i++) { bar_arrived[i] = 0; }
         for (;;) {
-            unsigned live = 0, waiting = 0;
+            unsigned live = 0;
+            const unsigned long long before = progress;
             for (unsigned t = 0; t < nthreads; t++) {
                 Fiber &f = fibers[t];
                 if (f.st == DONE) continue;
@@ -64,10 +87,10 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                 threadIdx_ = { t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
                 f.st = READY;
                 swapcontext(&sched_ctx, &f.ctx);
-                if (f.st != DONE) { live++; if (f.st == AT_BARRIER) waiting++; }
+                if (f.st != DONE) live++; else progress++;
             }
             if (live == 0) break;
-            if (waiting != live) { fprintf(stderr, "napa_emul: barrier divergence\n"); abort(); }
+            if (progress == before) { fprintf(stderr, "napa_emul: deadlock (threads wait on a barrier nobody completes)\n"); abort(); }
         }
     }
     free(sm);

@@ -39,6 +39,8 @@ extern dim3 blockDim_, gridDim_;
 extern unsigned char *dyn_smem;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 void syncthreads();
+void bar_sync(int id, unsigned count);      // named barrier (bar.sync id, count)
+void bar_arrive(int id, unsigned count);    // bar.arrive id, count
 }  // namespace napa_emul
 
 #define threadIdx (napa_emul::threadIdx_)
@@ -114,3 +116,12 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p 
 static inline void __threadfence() {}
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, const void *, int, size_t) { *n = 2; return cudaSuccess; }
+// the control warp of the pipeline kernel broadcasts a flag from lane 0; fibers run one at a
+// time, so emulate with a per-warp slot written by lane 0 (lane 0 always runs first in a round)
+namespace napa_emul { extern int shfl_slot[64]; }
+static inline int __shfl_sync(unsigned, int v, int src_lane) {
+    const unsigned tid = napa_emul::threadIdx_.x;
+    const unsigned warp = tid / 32, lane = tid % 32;
+    if ((int)lane == src_lane) napa_emul::shfl_slot[warp] = v;
+    return napa_emul::shfl_slot[warp];
+}
