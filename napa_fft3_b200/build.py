@@ -23,6 +23,7 @@ def build(force=False, verbose=False):
            "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-o", SO, SRC]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
+    cmd[1:1] = os.environ.get("NAPA_NVCC_EXTRA", "").split()
     subprocess.check_call(cmd)
     return SO
 

@@ -231,6 +231,7 @@ static int set_kernel_attrs() {
 static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStream_t st) {
     OK(ensure_stage_tw(l));
     p.stage_tw = G.stage_tw[l];
+    p.lg_tpi = ilog2((size_t)p.tiles_per_item); p.lg_G = ilog2((size_t)p.G);
     if (ntiles <= 0) return NAPA_OK;
     if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
     pass_fn fn = pass_kernel(l, kind);
@@ -280,13 +281,15 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     OK(ensure_stage_tw(lb));
     pp.a.stage_tw = G.stage_tw[la];
     pp.b.stage_tw = G.stage_tw[lb];
+    pp.a.lg_tpi = ilog2((size_t)pp.a.tiles_per_item); pp.a.lg_G = ilog2((size_t)pp.a.G);
+    pp.b.lg_tpi = ilog2((size_t)pp.b.tiles_per_item); pp.b.lg_G = ilog2((size_t)pp.b.G);
     const size_t smem = std::max(napa::kind_smem_bytes(la, napa::pipe_kind_a(pk)), napa::kind_smem_bytes(lb, napa::pipe_kind_b(pk)));
     static std::map<pipe_fn, int> occupancy;
     auto it = occupancy.find(fn);
     if (it == occupancy.end()) {
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la) + 32, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la), smem));
         if (nb < 1) return fail(NAPA_E_CUDA, "pipeline kernel does not fit on an SM");
         it = occupancy.emplace(fn, nb).first;
     }
@@ -301,7 +304,7 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
     const long long total_tiles = pp.items * pp.tiles_per_item * 2;
     long long grid = std::min<long long>((long long)G.num_sms * it->second, total_tiles);
-    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la) + 32, smem, st, pp);
+    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la), smem, st, pp);
     g_launches++;
     return NAPA_OK;
 }

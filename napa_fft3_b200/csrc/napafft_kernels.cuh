@@ -168,8 +168,9 @@ struct PassParams {
     long long src_batch_stride, dst_batch_stride;   // complex elements between batch items
     long long batch;                                // number of batch items in this launch
     int src_hint, dst_hint;                         // HINT_* L2 eviction hints of the data path
-    int tiles_per_item;                             // tiles inside one item (1 if PF_Q_IS_BATCH)
-    int G;                                          // tile r -> (r / G, r % G)
+    int tiles_per_item;                             // tiles inside one item (1 if PF_Q_IS_BATCH); a power of two
+    int G;                                          // tile r -> (r / G, r % G); a power of two
+    int lg_tpi, lg_G;                               // their logarithms (set by the launcher)
     long long s_SA, s_SG, s_i, s_q;                 // src offset = (r/G)*SA + (r%G)*SG + pos(i)*s_i + q*s_q
     long long d_SA, d_SG, d_i, d_q;
     unsigned flags;
@@ -303,6 +304,17 @@ __device__ __forceinline__ int smem_phys(int pos, int q) {
     if constexpr (PLANAR) return q * planar_pitch(LOG2L) + pos + (pos >> planar_padshift(LOG2L));
     else return ((pos + (pos >> plan_padshift(LOG2L))) << plan_log2c(LOG2L)) + q;
 }
+// smem_phys(t + m*T, q) - smem_phys(t, q): a compile-time constant whenever the padding period
+// divides T (then (t + m*T) >> PADSH == (t >> PADSH) + ((m*T) >> PADSH))
+template <int LOG2L, bool PLANAR>
+__device__ __forceinline__ int smem_delta(int t, int m) {
+    constexpr int T = (1 << LOG2L) / 16;
+    constexpr int PADSH = PLANAR ? planar_padshift(LOG2L) : plan_padshift(LOG2L);
+    constexpr int LOG2C = PLANAR ? 0 : plan_log2c(LOG2L);
+    if constexpr (PADSH >= 31) return (m * T) << LOG2C;
+    else if constexpr ((T & ((1 << PADSH) - 1)) == 0) return (m * T + ((m * T) >> PADSH)) << LOG2C;
+    else return ((m * T + (((t + m * T) >> PADSH) - (t >> PADSH))) << LOG2C);
+}
 // reorder buffer for bit-reversed row-side accesses: planar, low 3 position bits XOR reversed top 3
 template <int LOG2L>
 __device__ __forceinline__ int reorder_phys(int pos, int q) {
@@ -344,7 +356,9 @@ __device__ __forceinline__ void twiddle_powers(cplx (&v)[16], const int u, const
 // Stockham autosort stages.  Stage 0 runs under the load-side ids (t0, q0) and scatters; every
 // later stage gathers and runs under the store-side ids (t1, q1).  PRESYNC0: sm was used before
 // stage 0 (reorder of a bit-reversed load) and everyone must be done with it before the scatter.
-template <int LOG2L, int STAGE, int LOG2NS, bool PLANAR, bool PRESYNC0, class Sync>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+template <int LOG2L, int STAGE, int LOG2NS, bool PLANAR, bool PRESYNC0, class Sync, class Hook>
 struct Stages {
     static constexpr int L = 1 << LOG2L;
     static constexpr int T = L / 16;
@@ -355,12 +369,15 @@ struct Stages {
     static constexpr int NS = 1 << LOG2NS;
 
     static __device__ __forceinline__ void run(cplx (&v)[16], cplx *sm, const cplx *__restrict__ tw,
-                                               const int t0, const int q0, const int t1, const int q1) {
+                                               const int t0, const int q0, const int t1, const int q1, Hook &hook) {
         const int t = STAGE == 0 ? t0 : t1, q = STAGE == 0 ? q0 : q1;
         if constexpr (STAGE > 0) {
             // exchange: previous stage wrote its scattered outputs; gather t + m*T
+            // (one base address + compile-time offsets when the padding step divides T)
+            const cplx *g = sm + smem_phys<LOG2L, PLANAR>(t, q);
 #pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = sm[smem_phys<LOG2L, PLANAR>(t + m * T, q)];
+            for (int m = 0; m < 16; m++) v[m] = g[smem_delta<LOG2L, PLANAR>(t, m)];
+            if constexpr (STAGE + 1 == NSTAGES) hook();
             // twiddle W_{NS*R}^{(jb % NS) * s} on input s of butterfly jb = t + u*T.  Only the seed
             // w = W^{jb % NS} is loaded; its powers come from a product tree (depth <= 4): the
             // LSU<->register datapath, not the FP64 pipe, is the scarce resource of this kernel.
@@ -390,7 +407,7 @@ struct Stages {
                 for (int s = 0; s < R; s++) sm[smem_phys<LOG2L, PLANAR>(base + s * NS, q)] = v[u + s * NB];
             }
             Sync::sync();
-            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PLANAR, PRESYNC0, Sync>::run(v, sm, tw, t0, q0, t1, q1);
+            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PLANAR, PRESYNC0, Sync, Hook>::run(v, sm, tw, t0, q0, t1, q1, hook);
         }
     }
 };
@@ -431,9 +448,9 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
     constexpr int C = 1 << plan_log2c(LOG2L);
     TileCtx c;
     lane_ids<LOG2L, MAP>(threadIdx.x, c.t, c.q);
-    const long long b = tile / p.tiles_per_item;
-    const int r = (int)(tile - b * p.tiles_per_item);
-    const int ra = r / p.G, rg = r - ra * p.G;
+    const long long b = tile >> p.lg_tpi;
+    const int r = (int)(tile & (p.tiles_per_item - 1));
+    const int ra = r >> p.lg_G, rg = r & (p.G - 1);
     c.item = b;
     c.s_xoff = (long long)ra * p.s_SA + (long long)rg * p.s_SG;
     c.d_xoff = (long long)ra * p.d_SA + (long long)rg * p.d_SG;
@@ -455,10 +472,10 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 // All 16 data loads of a thread are issued back to back into v[], and every optional fusion is a
 // separate warp-uniform branch over the whole register array, so unused fusions cost nothing and
 // used ones do not serialise the loads.
-template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync = SyncAll, bool REUSE = false>
+template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
                                          const long long src_item_delta, const long long dst_item_delta,
-                                         const L2Policies &pol) {
+                                         const L2Policies &pol, Hook &hook) {
     constexpr int L = 1 << LOG2L;
     constexpr int T = L / 16;
     constexpr bool PLANAR = !(LM == MAP_Q && SM_ == MAP_Q);
@@ -490,8 +507,15 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
                 wv[m] = __ldg(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
             }
         }
+        if ((flags & PF_IN_REV) && !in_reorder) {
 #pragma unroll
-        for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)lpos(m) * s_i, src_hint, pol);
+            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i, src_hint, pol);
+        } else {
+            const cplx *s0 = src + (long long)t * s_i;
+            const long long step = (long long)T * s_i;
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(s0 + m * step, src_hint, pol);
+        }
         if (flags & PF_RIFFT_PRE) {
             // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177)
 #pragma unroll
@@ -548,10 +572,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 
     const TileCtx d = tile_ctx<LOG2L, SM_>(p, tile);
     if constexpr (REORDER_OK && LM == MAP_T) {
-        if (in_reorder) Stages<LOG2L, 0, 0, PLANAR, true, Sync>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
-        else Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+        if (in_reorder) Stages<LOG2L, 0, 0, PLANAR, true, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
+        else Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
     } else {
-        Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync>::run(v, sm, p.stage_tw, t, q, d.t, d.q);
+        Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
     }
 
     const bool out_reorder = REORDER_OK && SM_ == MAP_T && (flags & PF_OUT_REV);
@@ -580,8 +604,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 #pragma unroll
             for (int m = 0; m < 16; m++) st_data(dst + (long long)rev_bits(d.t + m * T, LOG2L) * d_i, v[m], dst_hint, pol);
         } else {
+            cplx *d0 = dst + (long long)d.t * d_i;
+            const long long step = (long long)T * d_i;
 #pragma unroll
-            for (int m = 0; m < 16; m++) st_data(dst + (long long)(d.t + m * T) * d_i, v[m], dst_hint, pol);
+            for (int m = 0; m < 16; m++) st_data(d0 + m * step, v[m], dst_hint, pol);
         }
     }
 }
@@ -616,7 +642,8 @@ __global__ void __launch_bounds__(plan_threads(LOG2L), plan_min_ctas(LOG2L))
 fft_pass_kernel(const PassParams p) {
     NAPA_DYN_SMEM(cplx, sm);
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
-    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND)>(p, (long long)blockIdx.x, sm, 0, 0, pol);
+    NoHook nh;
+    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND), SyncAll, false>(p, (long long)blockIdx.x, sm, 0, 0, pol, nh);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -631,6 +658,9 @@ fft_pass_kernel(const PassParams p) {
 // the slot it is about to overwrite.  Tickets are decoded two tiles ahead by one thread so that
 // the atomic, the decode and the dependency check stay off the critical path.
 // ------------------------------------------------------------------------------------------
+#ifndef NAPA_PIPE_COHERENT
+#define NAPA_PIPE_COHERENT true
+#endif
 struct PipeParams {
     PassParams a, b;                 // pass A (first executed) and pass B
     long long items;                 // batch
@@ -717,80 +747,68 @@ __device__ __forceinline__ void pipe_wait(const PipeWork &w, int *error) {
 __host__ __device__ constexpr int pipe_kind_a(int pk) { return pk == 2 ? 1 : 0; }
 __host__ __device__ constexpr int pipe_kind_b(int pk) { return pk == 0 ? 2 : (pk == 1 ? 1 : 0); }
 
-// Threads [0, NT) are compute warps; one extra CONTROL warp draws and decodes tickets two tiles
-// ahead, waits for dependencies and publishes completion (fence + atomic) -- all off the compute
-// warps' critical path.  Named barriers: 1 = compute warps only (exchanges), 2 = top of tile
-// (everyone), 3 = "stores of this tile issued" (compute warps arrive, control warp waits).
+// Thread 0 does the bookkeeping from a hook that runs in the MIDDLE of a tile (right after the
+// last exchange, before the final radix stage and the stores): there it publishes the completion
+// of the PREVIOUS tile (its stores were issued a whole tile ago, so the fence is cheap), decodes
+// the ticket two tiles ahead and checks the next tile's dependencies without blocking.  Nothing
+// but one barrier separates consecutive tiles on the compute warps' critical path.
 template <int LA, int LB, int PK>
-__global__ void __launch_bounds__(plan_threads(LA) + 32, plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
+__global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
     constexpr int KA = pipe_kind_a(PK), KB = pipe_kind_b(PK);
-    constexpr int NT = plan_threads(LA);
     NAPA_DYN_SMEM(cplx, sm);
     __shared__ PipeWork s_work[3];                   // ring: slot k%3 = k-th tile of this CTA
+    const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     const long long nphase = (long long)p.nchunks + p.lag;
     const long long total = pipe_prefix(p, nphase);
-    if (threadIdx.x >= NT) {
-        // ---------------- control warp ----------------
-        const bool lead = threadIdx.x == NT;
-        long long next_ticket = 0;
-        if (lead) {
-            PipeWork w0 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
-            PipeWork w1 = w0;
-            w1.tile = -1;
-            if (w0.tile >= 0) w1 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
-            if (w1.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
-            if (w0.tile >= 0 && !w0.ready) pipe_wait(w0, p.error);
-            s_work[0] = w0;
-            s_work[1] = w1;
-        }
-        bool pending = false;                        // completion of the previous tile not yet published
-        unsigned *pending_ctr = nullptr;
-        for (int k = 0;; k++) {
-            named_bar_sync(2, NT + 32);              // top of tile k: slots k and k+1 are published
-            const bool stop = s_work[k % 3].tile < 0;   // written by the lead lane >= 1 barrier ago
-            if (lead) {
-                if (pending) { __threadfence(); atomicAdd(pending_ctr, 1u); pending = false; }   // overlaps tile k
-                if (!stop) {
-                    const PipeWork cur = s_work[k % 3];
-                    const PipeWork nxt = s_work[(k + 1) % 3];
-                    PipeWork w;
-                    w.tile = -1;
-                    if (nxt.tile >= 0) {
-                        w = pipe_decode(p, next_ticket, nphase, total);
-                        if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
-                    }
-                    s_work[(k + 2) % 3] = w;
-                    pending_ctr = p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk;
-                }
-            }
-            if (stop) break;
-            named_bar_sync(3, NT + 32);              // compute warps have issued every store of tile k
-            if (lead) {
-                const PipeWork nxt = s_work[(k + 1) % 3];
-                const bool must_wait = nxt.tile >= 0 && nxt.dep && ld_acquire_u32(nxt.dep) < nxt.dep_target;
-                if (must_wait) {
-                    // the next tile may depend on this very tile: publish before blocking
-                    __threadfence(); atomicAdd(pending_ctr, 1u);
-                    pipe_wait(nxt, p.error);
-                } else {
-                    __threadfence();                 // acquire side of the non-blocking dependency check
-                    pending = true;
-                }
-            }
-        }
-        return;
+    const bool lead = threadIdx.x == 0;
+    long long next_ticket = 0;
+    unsigned *pending_ctr = nullptr;                 // completion counter of the previous tile, not yet published
+    if (lead) {
+        PipeWork w0 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
+        PipeWork w1 = w0;
+        w1.tile = -1;
+        if (w0.tile >= 0) w1 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
+        if (w1.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+        if (w0.tile >= 0 && !w0.ready) { pipe_wait(w0, p.error); w0.ready = 1; }
+        s_work[0] = w0;
+        s_work[1] = w1;
     }
-    // ---------------- compute warps ----------------
-    const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     for (int k = 0;; k++) {
-        named_bar_sync(2, NT + 32);
+        __syncthreads();                       // publishes slots k%3, (k+1)%3; previous tile is done with sm
         const PipeWork cur = s_work[k % 3];
         if (cur.tile < 0) break;
-        if (cur.is_a) run_tile<LA, true, kind_lm(LA, KA), kind_sm(LA, KA), SyncCompute<NT>, true>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, pol);
-        else run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncCompute<NT>, true>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, pol);
-        named_bar_arrive(3, NT + 32);
+        if (!cur.ready) {
+            // rare: dependencies were not yet satisfied at the mid-tile check.  This tile may depend
+            // on the previous tile of this very CTA, so publish that first, then block.
+            if (lead) {
+                if (pending_ctr) { __threadfence(); atomicAdd(pending_ctr, 1u); pending_ctr = nullptr; }
+                pipe_wait(cur, p.error);
+            }
+            __syncthreads();
+        }
+        auto hook = [&]() {
+            if (lead) {
+                if (pending_ctr) { __threadfence(); atomicAdd(pending_ctr, 1u); pending_ctr = nullptr; }
+                const PipeWork nxt = s_work[(k + 1) % 3];
+                PipeWork w;
+                w.tile = -1;
+                if (nxt.tile >= 0) {
+                    w = pipe_decode(p, next_ticket, nphase, total);
+                    if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+                    if (!nxt.ready && nxt.dep && ld_acquire_u32(nxt.dep) >= nxt.dep_target) {
+                        __threadfence();
+                        s_work[(k + 1) % 3].ready = 1;
+                    }
+                }
+                s_work[(k + 2) % 3] = w;
+            }
+        };
+        if (cur.is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, pol, hook);
+        else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, pol, hook);
+        if (lead) pending_ctr = p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk;
     }
+    if (lead && pending_ctr) { __threadfence(); atomicAdd(pending_ctr, 1u); }
 }
 
 // ------------------------------------------------------------------------------------------
