@@ -752,63 +752,90 @@ __host__ __device__ constexpr int pipe_kind_b(int pk) { return pk == 0 ? 2 : (pk
 // of the PREVIOUS tile (its stores were issued a whole tile ago, so the fence is cheap), decodes
 // the ticket two tiles ahead and checks the next tile's dependencies without blocking.  Nothing
 // but one barrier separates consecutive tiles on the compute warps' critical path.
+// Bookkeeping state of one persistent CTA.  It lives in shared memory and only thread 0 touches
+// it, so it costs the compute threads no registers across the tile body.
+struct PipeState {
+    PipeWork work[3];                // ring: slot k%3 = k-th tile of this CTA
+    long long next_ticket;
+    unsigned *pending;               // completion counter of the previous tile, not yet published
+};
+
+// out of line on purpose: inlined into the butterfly code it raised register pressure for every
+// thread; as a call, only thread 0 pays for it (once per tile)
+#ifdef NAPA_EMULATE
+#define NAPA_NOINLINE
+#else
+#define NAPA_NOINLINE __noinline__
+#endif
+__device__ NAPA_NOINLINE void pipe_bookkeeping(const PipeParams &p, PipeState *st, const int k) {
+    if (st->pending) { __threadfence(); atomicAdd(st->pending, 1u); st->pending = nullptr; }
+    const PipeWork nxt = st->work[(k + 1) % 3];
+    PipeWork w;
+    w.tile = -1;
+    if (nxt.tile >= 0) {
+        const long long nphase = (long long)p.nchunks + p.lag;
+        w = pipe_decode(p, st->next_ticket, nphase, pipe_prefix(p, nphase));
+        if (w.tile >= 0) st->next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+        if (!nxt.ready && nxt.dep && ld_acquire_u32(nxt.dep) >= nxt.dep_target) {
+            __threadfence();
+            st->work[(k + 1) % 3].ready = 1;
+        }
+    }
+    st->work[(k + 2) % 3] = w;
+}
+
+struct PipeHook {
+    const PipeParams &p;
+    PipeState *st;
+    int k;
+    __device__ __forceinline__ void operator()() const {
+        if (threadIdx.x == 0) pipe_bookkeeping(p, st, k);
+    }
+};
+
 template <int LA, int LB, int PK>
 __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
     constexpr int KA = pipe_kind_a(PK), KB = pipe_kind_b(PK);
     NAPA_DYN_SMEM(cplx, sm);
-    __shared__ PipeWork s_work[3];                   // ring: slot k%3 = k-th tile of this CTA
+    __shared__ PipeState st;
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
-    const long long nphase = (long long)p.nchunks + p.lag;
-    const long long total = pipe_prefix(p, nphase);
-    const bool lead = threadIdx.x == 0;
-    long long next_ticket = 0;
-    unsigned *pending_ctr = nullptr;                 // completion counter of the previous tile, not yet published
-    if (lead) {
+    if (threadIdx.x == 0) {
+        const long long nphase = (long long)p.nchunks + p.lag;
+        const long long total = pipe_prefix(p, nphase);
         PipeWork w0 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
         PipeWork w1 = w0;
         w1.tile = -1;
+        st.next_ticket = 0;
         if (w0.tile >= 0) w1 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
-        if (w1.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+        if (w1.tile >= 0) st.next_ticket = (long long)atomicAdd(p.ticket, 1ull);
         if (w0.tile >= 0 && !w0.ready) { pipe_wait(w0, p.error); w0.ready = 1; }
-        s_work[0] = w0;
-        s_work[1] = w1;
+        st.work[0] = w0;
+        st.work[1] = w1;
+        st.pending = nullptr;
     }
     for (int k = 0;; k++) {
         __syncthreads();                       // publishes slots k%3, (k+1)%3; previous tile is done with sm
-        const PipeWork cur = s_work[k % 3];
-        if (cur.tile < 0) break;
-        if (!cur.ready) {
+        const PipeWork *cw = &st.work[k % 3];
+        const long long tile = cw->tile;
+        if (tile < 0) break;
+        if (!cw->ready) {
             // rare: dependencies were not yet satisfied at the mid-tile check.  This tile may depend
             // on the previous tile of this very CTA, so publish that first, then block.
-            if (lead) {
-                if (pending_ctr) { __threadfence(); atomicAdd(pending_ctr, 1u); pending_ctr = nullptr; }
-                pipe_wait(cur, p.error);
+            if (threadIdx.x == 0) {
+                if (st.pending) { __threadfence(); atomicAdd(st.pending, 1u); st.pending = nullptr; }
+                pipe_wait(*cw, p.error);
             }
             __syncthreads();
         }
-        auto hook = [&]() {
-            if (lead) {
-                if (pending_ctr) { __threadfence(); atomicAdd(pending_ctr, 1u); pending_ctr = nullptr; }
-                const PipeWork nxt = s_work[(k + 1) % 3];
-                PipeWork w;
-                w.tile = -1;
-                if (nxt.tile >= 0) {
-                    w = pipe_decode(p, next_ticket, nphase, total);
-                    if (w.tile >= 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
-                    if (!nxt.ready && nxt.dep && ld_acquire_u32(nxt.dep) >= nxt.dep_target) {
-                        __threadfence();
-                        s_work[(k + 1) % 3].ready = 1;
-                    }
-                }
-                s_work[(k + 2) % 3] = w;
-            }
-        };
-        if (cur.is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false>(p.a, cur.tile, sm, 0, p.a_dst_is_ring ? cur.delta : 0, pol, hook);
-        else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false>(p.b, cur.tile, sm, p.b_src_is_ring ? cur.delta : 0, 0, pol, hook);
-        if (lead) pending_ctr = p.done + (cur.is_a ? 0 : p.nchunks) + cur.chunk;
+        const long long delta = cw->delta;
+        const bool is_a = cw->is_a != 0;
+        PipeHook hook{p, &st, k};
+        if (is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false>(p.a, tile, sm, 0, p.a_dst_is_ring ? delta : 0, pol, hook);
+        else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false>(p.b, tile, sm, p.b_src_is_ring ? delta : 0, 0, pol, hook);
+        if (threadIdx.x == 0) st.pending = p.done + (cw->is_a ? 0 : p.nchunks) + cw->chunk;
     }
-    if (lead && pending_ctr) { __threadfence(); atomicAdd(pending_ctr, 1u); }
+    if (threadIdx.x == 0 && st.pending) { __threadfence(); atomicAdd(st.pending, 1u); }
 }
 
 // ------------------------------------------------------------------------------------------
