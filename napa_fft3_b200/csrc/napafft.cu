@@ -74,8 +74,9 @@ struct State {
     void *dbuf[2] = {}; size_t dbuf_bytes = 0;
     void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = 32u << 20;       // per-launch chunk of the multi-launch fallback path
-    size_t pipe_chunk_bytes = 8u << 20;   // chunk of the persistent pipeline
-    int pipe_lag = 3;                     // phases between the two passes of a chunk
+    size_t pipe_chunk_bytes = 32u << 20;  // chunk of the persistent pipeline
+    int pipe_lag = 1;                     // phases between the two passes of a chunk
+    int pipe_group = 8;                   // tiles per ticket
     bool use_pipeline = true;
     bool attrs_set = false;
     int num_sms = 148;
@@ -302,7 +303,7 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     pp.error = G.d_error;
     if (const char *env = getenv("NAPAFFT_DEBUG")) pp.debug = atoi(env);
     if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
-    const long long total_tiles = pp.items * pp.tiles_per_item * 2;
+    const long long total_tiles = pp.items * pp.tiles_per_item * 2;      // in tickets
     long long grid = std::min<long long>((long long)G.num_sms * it->second, total_tiles);
     NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la), smem, st, pp);
     g_launches++;
@@ -431,7 +432,9 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         pchunk = std::min(pchunk, batch);
         pp.items = (long long)batch; pp.chunk = (int)pchunk; pp.nchunks = (int)((batch + pchunk - 1) / pchunk);
         pp.lag = std::max(1, G.pipe_lag);
-        pp.tiles_per_item = (long long)(n >> napa::plan_log2pts(d[0]));
+        pp.group = G.pipe_group;                                 // tiles per ticket (n >= 2^14: tiles per item >= 8)
+        while (pp.group > 1 && ((n >> napa::plan_log2pts(d[0])) % pp.group)) pp.group >>= 1;
+        pp.tiles_per_item = (long long)(n >> napa::plan_log2pts(d[0])) / pp.group;
         long long tpi;
         if (natural) {
             // A: column pass src -> scratch ring (+ inter-pass twiddle); B: row pass ring -> dst, transposed store
@@ -808,6 +811,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
+    if (const char *env = getenv("NAPAFFT_PIPE_GROUP")) G.pipe_group = std::max(1, atoi(env));
     if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
     G.num_sms = prop.multiProcessorCount;
     G.device = device;

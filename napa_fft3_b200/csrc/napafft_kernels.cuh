@@ -669,7 +669,8 @@ struct PipeParams {
     int lag;                         // phases between pass A and pass B of a chunk
     int slots;                       // scratch ring slots (0: intermediate lives in dst)
     int a_dst_is_ring, b_src_is_ring;
-    long long tiles_per_item;        // same for both passes (same tile shape)
+    long long tiles_per_item;        // TICKET units per item: one ticket = `group` adjacent tiles of one pass
+    int group;                       // tiles per ticket (bookkeeping is amortised over a group)
     unsigned long long *ticket;      // zeroed before launch
     unsigned *done;                  // [2][nchunks], zeroed before launch
     int *error;                      // set to 1 if a wait timed out (never expected)
@@ -724,7 +725,7 @@ __device__ __forceinline__ PipeWork pipe_decode(const PipeParams &p, const long 
         w.dep_target = (unsigned)(pipe_tilesum(p, c + 1) - pipe_tilesum(p, c));
     }
     if (w.dep) { w.ready = ld_acquire_u32(w.dep) >= w.dep_target; __threadfence(); }
-    w.tile = item0 * p.tiles_per_item + local;
+    w.tile = (item0 * p.tiles_per_item + local) * p.group;     // first tile of the group
     w.delta = p.slots ? (long long)(c % p.slots) * p.chunk - item0 : 0;
     w.chunk = (int)c;
     w.is_a = is_a ? 1 : 0;
@@ -760,14 +761,9 @@ struct PipeState {
     unsigned *pending;               // completion counter of the previous tile, not yet published
 };
 
-// out of line on purpose: inlined into the butterfly code it raised register pressure for every
-// thread; as a call, only thread 0 pays for it (once per tile)
-#ifdef NAPA_EMULATE
-#define NAPA_NOINLINE
-#else
-#define NAPA_NOINLINE __noinline__
-#endif
-__device__ NAPA_NOINLINE void pipe_bookkeeping(const PipeParams &p, PipeState *st, const int k) {
+// (measured: making this a real call is far worse -- the register save/restore around the call
+// site is paid by every thread)
+__device__ __forceinline__ void pipe_bookkeeping(const PipeParams &p, PipeState *st, const int k) {
     if (st->pending) { __threadfence(); atomicAdd(st->pending, 1u); st->pending = nullptr; }
     const PipeWork nxt = st->work[(k + 1) % 3];
     PipeWork w;
@@ -788,8 +784,9 @@ struct PipeHook {
     const PipeParams &p;
     PipeState *st;
     int k;
+    bool active;                     // only the last tile of a group does the bookkeeping
     __device__ __forceinline__ void operator()() const {
-        if (threadIdx.x == 0) pipe_bookkeeping(p, st, k);
+        if (active && threadIdx.x == 0) pipe_bookkeeping(p, st, k);
     }
 };
 
@@ -830,9 +827,13 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipel
         }
         const long long delta = cw->delta;
         const bool is_a = cw->is_a != 0;
-        PipeHook hook{p, &st, k};
-        if (is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false>(p.a, tile, sm, 0, p.a_dst_is_ring ? delta : 0, pol, hook);
-        else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false>(p.b, tile, sm, p.b_src_is_ring ? delta : 0, 0, pol, hook);
+        const int group = p.group;
+        for (int j = 0; j < group; j++) {
+            if (j) __syncthreads();            // previous tile of the group is done with sm
+            PipeHook hook{p, &st, k, j == group - 1};
+            if (is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false>(p.a, tile + j, sm, 0, p.a_dst_is_ring ? delta : 0, pol, hook);
+            else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false>(p.b, tile + j, sm, p.b_src_is_ring ? delta : 0, 0, pol, hook);
+        }
         if (threadIdx.x == 0) st.pending = p.done + (cw->is_a ? 0 : p.nchunks) + cw->chunk;
     }
     if (threadIdx.x == 0 && st.pending) { __threadfence(); atomicAdd(st.pending, 1u); }
