@@ -76,7 +76,7 @@ struct State {
     size_t chunk_bytes = 32u << 20;       // per-launch chunk of the multi-launch fallback path
     size_t pipe_chunk_bytes = 32u << 20;  // chunk of the persistent pipeline
     int pipe_lag = 1;                     // phases between the two passes of a chunk
-    int pipe_group = 8;                   // tiles per ticket
+    int pipe_group = 1;                   // tiles per ticket (>1 measured much slower: adjacent column tiles must be in flight together)
     bool use_pipeline = true;
     bool attrs_set = false;
     int num_sms = 148;
