@@ -114,6 +114,14 @@ int napafft_2rfft_dev(const void *v1, const void *v2, void *dst, size_t n, size_
 /* a[b*n + i] *= h[b*h_stride + i]  (pointwise spectrum product; h_stride 0 = shared filter) */
 int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, size_t h_stride, void *stream);
 
+/* Building blocks of the distributed four-step (single transforms >= 2^28 over several GPUs,
+ * SURVEY.md 8e): a transform along axis 0 of a row-major [n1][cols] device matrix, with the global
+ * twiddle W_M^{+-(col_offset + c) k1} (M = 2^lg_twiddle_modulus, 0 = none) fused into its last /
+ * first pass, and the [groups][rows][cols] <-> [rows][groups][cols] re-layout around the exchange. */
+int napafft_c2c_cols_dev(const void *src, void *dst, size_t n1, size_t cols, int dir, double scale,
+                         int lg_twiddle_modulus, long long col_offset, void *stream);
+int napafft_relayout_dev(const void *src, void *dst, size_t groups, size_t rows, size_t cols, int inverse, void *stream);
+
 /* plain device-memory helpers so that a non-CUDA host (SBCL) can hold device-resident vectors */
 int napafft_dev_alloc(void **out, size_t bytes);
 int napafft_dev_free(void *p);

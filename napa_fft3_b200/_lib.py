@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "napafft_c2c", "napafft_bit_reverse", "napafft_rfft", "napafft_rifft", "napafft_2rfft",
     "napafft_host_register", "napafft_host_unregister",
     "napafft_c2c_dev", "napafft_bit_reverse_dev", "napafft_rfft_dev", "napafft_rifft_dev", "napafft_2rfft_dev",
-    "napafft_cmul_dev", "napafft_dev_alloc", "napafft_dev_free", "napafft_dev_upload", "napafft_dev_download",
+    "napafft_cmul_dev", "napafft_c2c_cols_dev", "napafft_relayout_dev", "napafft_dev_alloc", "napafft_dev_free", "napafft_dev_upload", "napafft_dev_download",
     "napafft_dev_sync", "napafft_scale_factor", "napafft_radix2_twiddle",
 ]
 
@@ -65,6 +65,8 @@ class Binding:
         L.napafft_rifft_dev.argtypes = [vp, vp, sz, sz, i, vp]
         L.napafft_2rfft_dev.argtypes = [vp, vp, vp, sz, sz, i, vp]
         L.napafft_cmul_dev.argtypes = [vp, vp, sz, sz, sz, vp]
+        L.napafft_c2c_cols_dev.argtypes = [vp, vp, sz, sz, i, d, i, C.c_longlong, vp]
+        L.napafft_relayout_dev.argtypes = [vp, vp, sz, sz, sz, i, vp]
         L.napafft_dev_alloc.argtypes = [C.POINTER(vp), sz]
         L.napafft_dev_free.argtypes = [vp]
         L.napafft_dev_upload.argtypes = [vp, vp, sz]

@@ -353,6 +353,7 @@ static void pass_geometry(const std::vector<int> &d, int s, PassParams &p, long 
     }
     p.d_SA = p.s_SA; p.d_SG = p.s_SG; p.d_i = p.s_i; p.d_q = p.s_q;
     p.tiles_per_item = (int)*tiles_per_item;
+    p.tw_mul_t = 1; p.tw_mul_a = 0; p.tw_col_offset = 0; p.tw_col_shift = 0;
 }
 
 static void first_pass_fusions(PassParams &p, const C2COpts &o, size_t n, bool win_rev) {
@@ -554,6 +555,93 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         }
     }
     if (natural && !inv) OK(exec_bitrev(dst, dst, n, batch, dstride, dstride, NAPA_ELT_COMPLEX, st));
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Transform along axis 0 of a row-major [n1][cols] matrix (column passes only), used by the
+// distributed four-step: dst[k1][c] = sum_j1 src[j1][c] W_n1^{+-j1 k1}, optionally times the
+// global twiddle W_M^{+-(col_offset + c) * k1} (dir > 0: applied to the OUTPUT of the forward
+// transform; dir < 0: applied to the INPUT of the inverse transform).  Rows of dst are in natural
+// k1 order.  n1 = 2^4 .. 2^20, cols a multiple of the tile width.  src != dst.
+// ------------------------------------------------------------------------------------------
+static int exec_cols(const cplx *src, cplx *dst, size_t n1, size_t cols, int dir, double scale, int lgM,
+                     long long col_offset, cudaStream_t st) {
+    OK(set_kernel_attrs());
+    const int lg1 = ilog2(n1);
+    const bool inv = dir < 0;
+    std::vector<int> d;
+    if (lg1 <= 10) d = { lg1 };
+    else { int la = lg1 / 2; d = { la, lg1 - la }; }
+    for (int l : d) if (l < 4 || l > 10) return fail(NAPA_E_UNSUPPORTED, "column transform length 2^%d unsupported", lg1);
+    for (int l : d) if (cols % ((size_t)1 << napa::plan_log2c(l))) return fail(NAPA_E_UNSUPPORTED, "cols must be a multiple of %d", 1 << napa::plan_log2c(l));
+    BigTw gt{}; if (lgM > 0) OK(ensure_big_tw(lgM, &gt));
+    const long long B = (long long)cols;
+    auto global_tw = [&](PassParams &p, long long mul_t, long long mul_a) {
+        p.tw_lo = gt.lo; p.tw_hi = gt.hi; p.tw_shift = gt.shift; p.tw_mask = (1ull << lgM) - 1;
+        p.tw_col_offset = col_offset; p.tw_col_shift = 0; p.tw_mul_t = mul_t; p.tw_mul_a = mul_a;
+        p.flags |= inv ? napa::PF_TW_LOAD : napa::PF_TW_STORE;
+    };
+    if (d.size() == 1) {
+        const int l = d[0];
+        const long long C = 1LL << napa::plan_log2c(l);
+        PassParams p{};
+        p.src = src; p.dst = dst; p.batch = 1; p.G = (int)(B / C); p.tiles_per_item = p.G;
+        p.s_SA = 0; p.s_SG = C; p.s_i = B; p.s_q = 1;
+        p.d_SA = 0; p.d_SG = C; p.d_i = B; p.d_q = 1;
+        p.tw_mul_t = 1;
+        if (inv) p.flags |= napa::PF_CONJ_IN | napa::PF_CONJ_OUT;
+        if (scale != 1.0) { p.flags |= napa::PF_SCALE; p.scale = scale; }
+        if (lgM > 0) global_tw(p, 1, 0);
+        OK(launch_pass(l, KIND_COL, p, p.tiles_per_item, st));
+        CU(cudaGetLastError());
+        return NAPA_OK;
+    }
+    // two digits n1 = La * Lb.  Forward (DIF): digit a then digit b; row k1 = ka + La*kb.
+    // Inverse (DIT, mirror): digit b first (input rows k1 = ka + La*kb), then digit a.
+    const int la = d[0], lb = d[1];
+    const long long La = 1LL << la, Lb = 1LL << lb;
+    OK(ensure_scratch(n1 * cols * sizeof(cplx)));
+    BigTw it; OK(ensure_big_tw(lg1, &it));
+    PassParams pa{}, pb{};
+    // digit a over the [La][Lb*B] view, intra twiddle W_n1^{ka * jb}, jb = col / B
+    {
+        const long long C = 1LL << napa::plan_log2c(la);
+        pa.batch = 1; pa.G = (int)((Lb * B) / C); pa.tiles_per_item = pa.G;
+        pa.s_SA = 0; pa.s_SG = C; pa.s_i = Lb * B; pa.s_q = 1;
+        pa.d_SA = 0; pa.d_SG = C; pa.d_i = Lb * B; pa.d_q = 1;
+        pa.tw_lo = it.lo; pa.tw_hi = it.hi; pa.tw_shift = it.shift; pa.tw_mask = (1ull << lg1) - 1;
+        pa.tw_mul_t = 1; pa.tw_mul_a = 0; pa.tw_col_offset = 0; pa.tw_col_shift = ilog2((size_t)B);
+    }
+    // digit b over the [La][Lb][B] view (A = La tiles rows), natural row order on the k1 side:
+    // position (ka, kb) <-> row ka + La*kb
+    {
+        const long long C = 1LL << napa::plan_log2c(lb);
+        pb.batch = 1; pb.G = (int)(B / C); pb.tiles_per_item = (int)(La * (B / C));
+        pb.s_SA = Lb * B; pb.s_SG = C; pb.s_i = B; pb.s_q = 1;
+        pb.d_SA = Lb * B; pb.d_SG = C; pb.d_i = B; pb.d_q = 1;
+        pb.tw_mul_t = 1;
+    }
+    if (!inv) {
+        pa.src = src; pa.dst = G.scratch; pa.flags |= napa::PF_TW_STORE;
+        if (scale != 1.0) { pa.flags |= napa::PF_SCALE; pa.scale = scale; }
+        pb.src = G.scratch; pb.dst = dst;
+        pb.d_SA = B; pb.d_i = La * B;                       // store row ka + La*kb
+        if (lgM > 0) global_tw(pb, La, 1);                   // k1 = ra + La*(t + m*T)
+        OK(launch_pass(la, KIND_COL, pa, pa.tiles_per_item, st));
+        OK(launch_pass(lb, KIND_COL, pb, pb.tiles_per_item, st));
+    } else {
+        // DIT mirror: first the b digit, reading rows k1 = ka + La*kb, global twiddle on its load
+        pb.src = src; pb.dst = G.scratch;
+        pb.s_SA = B; pb.s_i = La * B;
+        pb.flags |= napa::PF_CONJ_IN;
+        if (scale != 1.0) { pb.flags |= napa::PF_SCALE; pb.scale = scale; }
+        if (lgM > 0) global_tw(pb, La, 1);
+        pa.src = G.scratch; pa.dst = dst; pa.flags |= napa::PF_TW_LOAD | napa::PF_CONJ_OUT;
+        OK(launch_pass(lb, KIND_COL, pb, pb.tiles_per_item, st));
+        OK(launch_pass(la, KIND_COL, pa, pa.tiles_per_item, st));
+    }
     CU(cudaGetLastError());
     return NAPA_OK;
 }
@@ -918,6 +1006,32 @@ NAPA_API int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, si
                 (const cplx *)h, (long long)n, (long long)batch, (long long)h_stride);
     g_launches++;
     CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+NAPA_API int napafft_c2c_cols_dev(const void *src, void *dst, size_t n1, size_t cols, int dir, double scale,
+                                  int lg_twiddle_modulus, long long col_offset, void *stream) {
+    if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (src == dst) return fail(NAPA_E_UNSUPPORTED, "column transform is out of place");
+    if (!pow2(n1) || !pow2(cols)) return fail(NAPA_E_NOT_POW2, "n1 = %zu / cols = %zu must be powers of two", n1, cols);
+    if (dir != NAPA_FWD && dir != NAPA_INV) return fail(NAPA_E_BAD_ENUM, "direction %d is not 1 / -1", dir);
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    return exec_cols((const cplx *)src, (cplx *)dst, n1, cols, dir, scale, lg_twiddle_modulus, col_offset, (cudaStream_t)stream);
+}
+
+// dst[r][g][c] = src[g][r][c]   (g < groups, r < rows, c < cols): re-layout around the all-to-all
+NAPA_API int napafft_relayout_dev(const void *src, void *dst, size_t groups, size_t rows, size_t cols, int inverse, void *stream) {
+    if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    OK(ensure_init());
+    for (size_t g = 0; g < groups; g++) {
+        if (!inverse)
+            CU(cudaMemcpy2DAsync((char *)dst + g * cols * 16, groups * cols * 16, (const char *)src + g * rows * cols * 16, cols * 16,
+                                 cols * 16, rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        else
+            CU(cudaMemcpy2DAsync((char *)dst + g * rows * cols * 16, cols * 16, (const char *)src + g * cols * 16, groups * cols * 16,
+                                 cols * 16, rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
     return NAPA_OK;
 }
 

@@ -182,6 +182,10 @@ struct PassParams {
     const cplx *tw_lo, *tw_hi;                      // W_M^e = hi[e >> tw_shift] * lo[e & mask]
     int tw_shift;
     unsigned long long tw_mask;                     // M - 1
+    // exponent of register m = colx * (tw_mul_a * ra + tw_mul_t * (t + m*T)),  colx = tw_col_offset + (col >> tw_col_shift)
+    // (plain passes: tw_mul_t = 1, tw_mul_a = 0, offset 0, shift 0)
+    long long tw_col_offset, tw_mul_t, tw_mul_a;
+    int tw_col_shift;
     const cplx *r2tw;                               // reference recurrence table (rifft pre-pass)
     long long aux_off;                              // N for PF_RIFFT_PRE
 };
@@ -416,9 +420,11 @@ struct Stages {
 //   B = W^{t*col}, D = W^{T*col};  P_m = B * D^m  built from D^2, D^4, D^8.
 // 18 complex products instead of 32 dependent table look-ups; every seed load is issued at once.
 template <int T>
-__device__ __forceinline__ void apply_big_twiddle(cplx (&v)[16], const PassParams &p, int t, unsigned col) {
-    const unsigned long long eb = ((unsigned long long)t * col) & p.tw_mask;
-    const unsigned long long ed = ((unsigned long long)T * col) & p.tw_mask;
+__device__ __forceinline__ void apply_big_twiddle(cplx (&v)[16], const PassParams &p, int t, unsigned col, int ra) {
+    const unsigned long long colx = (unsigned long long)(p.tw_col_offset + (long long)(col >> p.tw_col_shift)) & p.tw_mask;
+    const unsigned long long idx = ((unsigned long long)(p.tw_mul_a * ra + p.tw_mul_t * t)) & p.tw_mask;
+    const unsigned long long eb = (idx * colx) & p.tw_mask;
+    const unsigned long long ed = ((((unsigned long long)(p.tw_mul_t * T)) & p.tw_mask) * colx) & p.tw_mask;
     const unsigned long long lomask = (1ull << p.tw_shift) - 1;
     const cplx blo = ldg_c(p.tw_lo + (eb & lomask)), bhi = ldg_c(p.tw_hi + (eb >> p.tw_shift));
     const cplx dlo = ldg_c(p.tw_lo + (ed & lomask)), dhi = ldg_c(p.tw_hi + (ed >> p.tw_shift));
@@ -442,6 +448,7 @@ struct TileCtx {
     bool valid;
     long long s_xoff, d_xoff;
     unsigned col;                    // column offset inside the [L][B] sub-matrix (twiddle exponent)
+    int ra;                          // outer index of the tile (twiddle exponent of distributed passes)
 };
 template <int LOG2L, int MAP>
 __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long tile) {
@@ -462,6 +469,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
     }
     c.valid = c.item < p.batch;
     c.col = (unsigned)(rg * C + c.q);
+    c.ra = ra;
     return c;
 }
 
@@ -568,7 +576,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             for (int m = 0; m < 16; m++) v[m] = sm[reorder_phys<LOG2L>(rev_bits(t + m * T, LOG2L), q)];
         }
     }
-    if (c.valid && (flags & PF_TW_LOAD)) apply_big_twiddle<T>(v, p, t, c.col);
+    if (c.valid && (flags & PF_TW_LOAD)) apply_big_twiddle<T>(v, p, t, c.col, c.ra);
 
     const TileCtx d = tile_ctx<LOG2L, SM_>(p, tile);
     if constexpr (REORDER_OK && LM == MAP_T) {
@@ -580,7 +588,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 
     const bool out_reorder = REORDER_OK && SM_ == MAP_T && (flags & PF_OUT_REV);
     if (d.valid) {
-        if (flags & PF_TW_STORE) apply_big_twiddle<T>(v, p, d.t, d.col);
+        if (flags & PF_TW_STORE) apply_big_twiddle<T>(v, p, d.t, d.col, d.ra);
         if (flags & PF_CONJ_OUT) {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m].y = -v[m].y;

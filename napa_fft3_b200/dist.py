@@ -41,3 +41,95 @@ def max_over_ranks(value: float, dist=None, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class DistributedFFT:
+    """One complex-double transform of N = 2^lgN points spread over the P ranks of a
+    torch.distributed group (BASELINE config C5): the four-step N = N1*N2 with ONE
+    all-to-all.
+
+    Layouts (both are "column blocks of a row-major matrix"; no rank ever holds the whole vector):
+      time  side: x[j1*N2 + j2] viewed as [N1][N2];  rank g holds columns j2 in [g*B, (g+1)*B),
+                  B = N2/P, as a contiguous local [N1][B] array;
+      freq  side: X[k1 + N1*k2] viewed as [N1][N2] (k1 = row); rank h holds rows k1 in
+                  [h*R, (h+1)*R), R = N1/P, as a contiguous local [R][N2] array (k2 natural).
+    forward():  local column FFTs over j1 with the twiddle W_N^{j2 k1} fused into the last column
+                pass -> all-to-all of contiguous [R][B] slabs -> re-layout -> local row FFTs over j2.
+    inverse():  the same steps backwards (unscaled row inverse, exchange, twiddled column inverse
+                with the 1/N scale fused into its first load).
+    Device work goes through the C ABI (napafft_c2c_cols_dev / napafft_relayout_dev /
+    napafft_c2c_dev); torch.distributed (NCCL over NVLink, or gloo on CPU in the tests) carries the
+    exchange.
+    """
+
+    def __init__(self, lgN, binding, dist, device, stream=None):
+        import torch
+        self.torch, self.b, self.dist, self.device = torch, binding, dist, device
+        self.P = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.P > 1 else 0
+        self.lgN = lgN
+        self.lg1 = lgN // 2
+        self.N1, self.N2 = 1 << self.lg1, 1 << (lgN - self.lg1)
+        if self.N1 % self.P or self.N2 % self.P:
+            raise ValueError("P must divide both N1 and N2")
+        self.B, self.R = self.N2 // self.P, self.N1 // self.P
+        self._stream = stream
+        mk = lambda *shape: torch.empty(shape, dtype=torch.complex128, device=device)
+        self.send = mk(self.N1, self.B)
+        self.recv = mk(self.N1, self.B)
+        self.rows = mk(self.R, self.N2)
+
+    def _st(self):
+        if self._stream is not None:
+            return self._stream
+        if self.device.type == "cuda":
+            return self.torch.cuda.current_stream().cuda_stream
+        return None
+
+    def _exchange(self, out, inp):
+        """all-to-all of P contiguous equal slabs (complex as pairs of doubles: NCCL has no complex type)"""
+        if self.P == 1:
+            out.copy_(inp)
+            return
+        self.dist.all_to_all_single(self.torch.view_as_real(out).view(-1), self.torch.view_as_real(inp).view(-1))
+
+    def forward(self, x_local, out=None):
+        """x_local: [N1][B] complex128 (time layout) -> [R][N2] (freq layout), unscaled."""
+        t = self.torch
+        assert x_local.shape == (self.N1, self.B) and x_local.dtype == t.complex128 and x_local.is_contiguous()
+        out = t.empty((self.R, self.N2), dtype=t.complex128, device=self.device) if out is None else out
+        st = self._st()
+        self.b.c2c_cols_dev(x_local.data_ptr(), self.send.data_ptr(), self.N1, self.B, 1, 1.0, self.lgN,
+                            self.rank * self.B, st)
+        self._exchange(self.recv, self.send)                       # recv = [P][R][B]
+        self.b.relayout_dev(self.recv.data_ptr(), self.rows.data_ptr(), self.P, self.R, self.B, 0, st)   # -> [R][P][B]
+        self.b.c2c_dev(self.rows.data_ptr(), out.data_ptr(), self.N2, self.R, self.N2, 1, 0, 1, None, 0, 0, st)
+        return out
+
+    def inverse(self, X_local, out=None):
+        """X_local: [R][N2] (freq layout) -> [N1][B] (time layout), scaled by 1/N."""
+        t = self.torch
+        assert X_local.shape == (self.R, self.N2) and X_local.dtype == t.complex128 and X_local.is_contiguous()
+        out = t.empty((self.N1, self.B), dtype=t.complex128, device=self.device) if out is None else out
+        st = self._st()
+        self.b.c2c_dev(X_local.data_ptr(), self.rows.data_ptr(), self.N2, self.R, self.N2, -1, 0, 1, None, 0, 0, st)
+        self.b.relayout_dev(self.rows.data_ptr(), self.send.data_ptr(), self.P, self.R, self.B, 1, st)   # -> [P][R][B]
+        self._exchange(self.recv, self.send)                       # recv = [N1][B], rows k1 natural
+        self.b.c2c_cols_dev(self.recv.data_ptr(), out.data_ptr(), self.N1, self.B, -1, 1.0 / float(1 << self.lgN),
+                            self.lgN, self.rank * self.B, st)
+        return out
+
+    # helpers for tests / host callers: cut a full host vector into this rank's local arrays
+    def scatter_time(self, x_full):
+        m = np.asarray(x_full).reshape(self.N1, self.N2)
+        return np.ascontiguousarray(m[:, self.rank * self.B:(self.rank + 1) * self.B])
+
+    def freq_index(self):
+        """global bin index k of every element of the local freq-side array"""
+        k1 = (self.rank * self.R + np.arange(self.R))[:, None]
+        k2 = np.arange(self.N2)[None, :]
+        return k1 + self.N1 * k2
+
+    def alltoall_bytes_per_rank(self):
+        """bytes each rank sends (= receives) over the interconnect per transform"""
+        return (self.P - 1) * self.R * self.B * 16

@@ -70,3 +70,49 @@ def test_batch_sharding_world2_gloo():
         assert err <= 1e-12 and rt <= 1e-12
         assert t == 2.0                                      # max over ranks
         assert shape == (13, 1024)
+
+
+def _dist_fft_worker(rank, world, port, q, lgN):
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from emul.build_emul import build
+    from napa_fft3_b200 import Binding
+    from napa_fft3_b200.dist import DistributedFFT
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = Binding(build()); b.init(0)
+    N = 1 << lgN
+    rng = np.random.Generator(np.random.Philox(1005))
+    x = rng.uniform(-1, 1, N) + 1j * rng.uniform(-1, 1, N)           # same vector on every rank
+    ref = np.fft.fft(x)
+    f = DistributedFFT(lgN, b, dist, torch.device("cpu"))
+    xl = torch.from_numpy(f.scatter_time(x))
+    Xl = f.forward(xl)
+    err_f = np.linalg.norm(Xl.numpy() - ref[f.freq_index()]) / np.linalg.norm(ref[f.freq_index()])
+    back = f.inverse(Xl)
+    err_b = np.linalg.norm(back.numpy() - f.scatter_time(x)) / np.linalg.norm(f.scatter_time(x))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, float(err_f), float(err_b), f.alltoall_bytes_per_rank()))
+
+
+@pytest.mark.parametrize("lgN", [16, 21])
+def test_distributed_four_step_world2_gloo(lgN):
+    """config C5 in miniature: one transform over 2 ranks, one all-to-all, vs numpy's DFT"""
+    import torch.multiprocessing as mp
+    from emul.build_emul import build
+    build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + lgN
+    procs = [ctx.Process(target=_dist_fft_worker, args=(r, 2, port, q, lgN)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ef, eb, nbytes in res:
+        assert ef <= 1e-13 * lgN and eb <= 1e-13 * lgN, (rank, ef, eb)
+        assert nbytes == (1 << lgN) * 16 // 4                      # (P-1)/P * 16 N / P with P = 2
