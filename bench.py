@@ -31,13 +31,15 @@ WORKLOADS = {
     "c2": (1 << 16, 4096, "4096 x 2^16 complex doubles: windowed-fft (shared Hann, :in-order t) -> ifft :scale :inv"),
     "c3": (1 << 20, 1024, "1024 x 2^20: fft :in-order nil -> ifft :in-order nil :window H (shared complex filter)"),
     "c4": (1 << 14, 8192, "8192 x 2^14 reals: rfft :scale nil -> rifft :scale t"),
+    # one transform spread over all ranks (distributed four-step, one all-to-all); strong scaling
+    "c5": (1 << 30, 1, "single 2^30-point c2c, distributed four-step, all-to-all over NVLink"),
 }
 
 
 def flops_per_step(wl):
     n, batch, _ = WORKLOADS[wl]
     lg = np.log2(n)
-    if wl == "c1":
+    if wl in ("c1", "c5"):
         return 5.0 * n * lg * batch
     if wl == "c4":
         return 2 * 2.5 * n * lg * batch
@@ -47,7 +49,7 @@ def flops_per_step(wl):
 def algorithmic_bytes_per_step(wl):
     """c2c 32 N B per transform (+ shared window once), rfft/rifft 24 N."""
     n, batch, _ = WORKLOADS[wl]
-    if wl == "c1":
+    if wl in ("c1", "c5"):
         return 32.0 * n * batch
     if wl == "c4":
         return 2 * 24.0 * n * batch
@@ -225,6 +227,9 @@ def main():
 
     wl = args.workload
     n, batch, desc = WORKLOADS[wl]
+    if wl == "c5":
+        run_c5(args, torch, dist, napa, b, world, rank, local, dev)
+        return
     stream = torch.cuda.current_stream().cuda_stream
     g = torch.Generator(device=dev); g.manual_seed(1002 + rank)
 
@@ -367,6 +372,88 @@ def main():
                        "sharding": "batch-sharded, no collective" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity_nre_vs_oracle": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_c5(args, torch, dist, napa, b, world, rank, local, dev):
+    """BASELINE config C5: ONE 2^lg transform over all ranks (strong scaling: total work fixed).
+    Device-resident distributed layouts (napa_fft3_b200.dist.DistributedFFT); time = max over ranks."""
+    from napa_fft3_b200.dist import DistributedFFT
+    lg = int(os.environ.get("NAPAFFT_C5_LOG2N", "30"))
+    n = 1 << lg
+    f = DistributedFFT(lg, b, dist if world > 1 else None, dev)
+    g = torch.Generator(device=dev); g.manual_seed(1005 + rank)
+    x = torch.view_as_complex(torch.rand((f.N1, f.B, 2), dtype=torch.float64, device=dev, generator=g) * 2 - 1).contiguous()
+    out = torch.empty((f.R, f.N2), dtype=torch.complex128, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        f.forward(x, out)
+    barrier()
+    sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
+    launches0 = b.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        f.forward(x, out)
+    e1.record()
+    barrier()
+    t_end = time.perf_counter()
+    launches = b.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_begin, t_end)
+    # exchange alone (same buffers), for the NVLink roofline
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a0.record()
+    for _ in range(args.steps):
+        f._exchange(f.recv, f.send)
+    a1.record()
+    barrier()
+    a2a_ms = a0.elapsed_time(a1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms, a2a_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, a2a_ms = t[0].item(), t[1].item()
+    ms_per_step = ms / args.steps
+    # parity: round trip + a sample of bins against a direct DFT of the (regenerated) input is
+    # done in tests/tools (dist_check.py); here only the round-trip residual
+    back = f.inverse(out)
+    rt = (torch.linalg.norm(back - x) / torch.linalg.norm(x)).item()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_bytes = 32.0 * n / world                      # compulsory HBM bytes per GPU
+        a2a_bytes = f.alltoall_bytes_per_rank()
+        line = {
+            "metric": "fp64_complex_fft_gflops", "value": 5.0 * n * lg / (ms_per_step * 1e-3) / 1e9, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c5", "description": WORKLOADS["c5"][2], "n": n, "N1": f.N1, "N2": f.N2,
+                       "layout": "time side: column block of [N1][N2]; freq side: row block k1 of X[k1 + N1*k2]",
+                       "l2_policy": "inputs_exceed_l2 (%.1f GiB per GPU)" % (16.0 * n / world / 2**30)},
+            "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": hbm_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None,
+                         "note": "per-GPU compulsory bytes (32 N / P) over the whole step, all-to-all included"},
+            "nvlink": {"alltoall_bytes_per_gpu_each_way": a2a_bytes, "alltoall_ms": a2a_ms,
+                       "achieved_gbs_per_direction": (a2a_bytes / (a2a_ms * 1e-3) / 1e9) if a2a_ms > 0 and world > 1 else None,
+                       "peak_measured_ref": 770.0, "peak_nominal": 900.0,
+                       "frac_of_measured": (a2a_bytes / (a2a_ms * 1e-3) / 1e9 / 770.0) if a2a_ms > 0 and world > 1 else None},
+            "cpu_baseline": None, "round_trip_nre": rt,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

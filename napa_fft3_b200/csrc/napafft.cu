@@ -74,9 +74,9 @@ struct State {
     void *dbuf[2] = {}; size_t dbuf_bytes = 0;
     void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = 32u << 20;       // per-launch chunk of the multi-launch fallback path
-    size_t pipe_chunk_bytes = 32u << 20;  // chunk of the persistent pipeline
-    int pipe_lag = 1;                     // phases between the two passes of a chunk
-    int pipe_group = 1;                   // tiles per ticket (>1 measured much slower: adjacent column tiles must be in flight together)
+    size_t pipe_chunk_bytes = 4u << 20;   // chunk of the persistent pipeline (small: the scratch ring must stay in L2)
+    int pipe_lag = 0;                     // phases between the two passes of a chunk (0 = auto)
+    int pipe_slots = 0;                   // scratch ring slots (0 = auto)
     bool use_pipeline = true;
     bool attrs_set = false;
     int num_sms = 148;
@@ -275,6 +275,42 @@ static int ensure_counters(cudaStream_t st, size_t bytes, unsigned char **out) {
     return NAPA_OK;
 }
 
+// resident CTAs of a pipeline kernel (cached)
+static int pipeline_resident(int la, int lb, int pk, long long *out) {
+    pipe_fn fn = pipe_kernel(la, lb, pk);
+    if (!fn) return fail(NAPA_E_UNSUPPORTED, "no pipeline kernel for digits (%d, %d)", la, lb);
+    static std::map<pipe_fn, int> occ;
+    auto it = occ.find(fn);
+    if (it == occ.end()) {
+        const size_t smem = std::max(napa::kind_smem_bytes(la, napa::pipe_kind_a(pk)), napa::kind_smem_bytes(lb, napa::pipe_kind_b(pk)));
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la), smem));
+        if (nb < 1) return fail(NAPA_E_CUDA, "pipeline kernel does not fit on an SM");
+        it = occ.emplace(fn, nb).first;
+    }
+    *out = (long long)G.num_sms * it->second;
+    return NAPA_OK;
+}
+
+// Chunking of the persistent pipeline.  With W resident CTAs and T tickets per chunk and pass,
+// tickets run  A(c) | A(c+1) B(c+1-lag) | ...  A tile of B(c) must not be drawn while A(c) tiles
+// are still in flight, and (scratch ring) an A(c) tile must not be drawn while B(c - slots) still
+// drains the slot: both ticket distances, 2T*lag and 2T*(slots - lag - 1), are kept >= 1.5 W.
+// Chunks are small (default 4 MiB) so that the ring (slots chunks, about 2.5 * W tiles) stays in L2.
+static void pipeline_shape(long long W, size_t n, size_t batch, int lg_tile_pts, bool ring, napa::PipeParams &pp) {
+    size_t pchunk = std::max<size_t>(1, G.pipe_chunk_bytes / (n * sizeof(cplx)));
+    pchunk = std::min(pchunk, batch);
+    const long long T = (long long)pchunk * (long long)(n >> lg_tile_pts);
+    long long k = (3 * W / 2 + 2 * T - 1) / (2 * T);
+    if (k < 1) k = 1;
+    pp.items = (long long)batch; pp.chunk = (int)pchunk; pp.nchunks = (int)((batch + pchunk - 1) / pchunk);
+    pp.lag = G.pipe_lag > 0 ? G.pipe_lag : (int)k;
+    pp.slots = ring ? (G.pipe_slots > 0 ? G.pipe_slots : pp.lag + 1 + (int)k) : 0;
+    pp.group = 1;
+    pp.tiles_per_item = (long long)(n >> lg_tile_pts);
+}
+
 static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStream_t st) {
     pipe_fn fn = pipe_kernel(la, lb, pk);
     if (!fn) return fail(NAPA_E_UNSUPPORTED, "no pipeline kernel for digits (%d, %d)", la, lb);
@@ -285,15 +321,8 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     pp.a.lg_tpi = ilog2((size_t)pp.a.tiles_per_item); pp.a.lg_G = ilog2((size_t)pp.a.G);
     pp.b.lg_tpi = ilog2((size_t)pp.b.tiles_per_item); pp.b.lg_G = ilog2((size_t)pp.b.G);
     const size_t smem = std::max(napa::kind_smem_bytes(la, napa::pipe_kind_a(pk)), napa::kind_smem_bytes(lb, napa::pipe_kind_b(pk)));
-    static std::map<pipe_fn, int> occupancy;
-    auto it = occupancy.find(fn);
-    if (it == occupancy.end()) {
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la), smem));
-        if (nb < 1) return fail(NAPA_E_CUDA, "pipeline kernel does not fit on an SM");
-        it = occupancy.emplace(fn, nb).first;
-    }
+    long long W;
+    OK(pipeline_resident(la, lb, pk, &W));
     const size_t cbytes = 16 + 2 * (size_t)pp.nchunks * sizeof(unsigned);
     unsigned char *ctr;
     OK(ensure_counters(st, cbytes, &ctr));
@@ -304,7 +333,7 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     if (const char *env = getenv("NAPAFFT_DEBUG")) pp.debug = atoi(env);
     if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
     const long long total_tiles = pp.items * pp.tiles_per_item * 2;      // in tickets
-    long long grid = std::min<long long>((long long)G.num_sms * it->second, total_tiles);
+    long long grid = std::min<long long>(W, total_tiles);
     NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la), smem, st, pp);
     g_launches++;
     return NAPA_OK;
@@ -429,17 +458,15 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                           napa::plan_log2pts(d[0]) == napa::plan_log2pts(d[1]);   // one tile shape per pipeline
     if (can_pipe) {
         napa::PipeParams pp{};
-        size_t pchunk = std::max<size_t>(1, G.pipe_chunk_bytes / (n * sizeof(cplx)));
-        pchunk = std::min(pchunk, batch);
-        pp.items = (long long)batch; pp.chunk = (int)pchunk; pp.nchunks = (int)((batch + pchunk - 1) / pchunk);
-        pp.lag = std::max(1, G.pipe_lag);
-        pp.group = G.pipe_group;                                 // tiles per ticket (n >= 2^14: tiles per item >= 8)
-        while (pp.group > 1 && ((n >> napa::plan_log2pts(d[0])) % pp.group)) pp.group >>= 1;
-        pp.tiles_per_item = (long long)(n >> napa::plan_log2pts(d[0])) / pp.group;
+        const int pk = natural ? 0 : (inv ? 2 : 1);
+        const int la = pk == 2 ? d[1] : d[0], lb = pk == 2 ? d[0] : d[1];
+        long long W;
+        OK(pipeline_resident(la, lb, pk, &W));
+        pipeline_shape(W, n, batch, napa::plan_log2pts(d[0]), natural, pp);
+        const size_t pchunk = (size_t)pp.chunk;
         long long tpi;
         if (natural) {
             // A: column pass src -> scratch ring (+ inter-pass twiddle); B: row pass ring -> dst, transposed store
-            pp.slots = pp.lag + 2;
             OK(ensure_scratch((size_t)pp.slots * pchunk * n * sizeof(cplx)));
             BigTw bt; OK(ensure_big_tw(lg, &bt));
             PassParams &p1 = pp.a, &p2 = pp.b;
@@ -460,7 +487,6 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             OK(launch_pipeline(d[0], d[1], 0, pp, st));
         } else {
             // bit-reversed layouts: in place on dst after the first pass, no scratch
-            pp.slots = 0;
             const int sa = inv ? 1 : 0, sb = inv ? 0 : 1;      // DIT runs the digits last to first
             BigTw bt; OK(ensure_big_tw(lg, &bt));
             PassParams *ps[2] = { &pp.a, &pp.b };
@@ -899,7 +925,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
-    if (const char *env = getenv("NAPAFFT_PIPE_GROUP")) G.pipe_group = std::max(1, atoi(env));
+    if (const char *env = getenv("NAPAFFT_PIPE_SLOTS")) G.pipe_slots = atoi(env);
     if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
     G.num_sms = prop.multiProcessorCount;
     G.device = device;

@@ -166,3 +166,23 @@ def test_launch_counter_moves(napa):
     before = b.launch_count()
     napa.fft(np.arange(1024, dtype=np.complex128))
     assert b.launch_count() > before
+
+
+@pytest.mark.parametrize("lgN", [16, 22, 26])
+def test_distributed_building_blocks_single_rank(napa, lgN):
+    """the device kernels of the distributed four-step (column-axis transform with fused global
+    twiddle, re-layout, batched rows) on one GPU: P = 1 makes the exchange a copy"""
+    import torch
+    import napa_fft3_b200 as P
+    from napa_fft3_b200.dist import DistributedFFT
+    dev = torch.device("cuda:0")
+    f = DistributedFFT(lgN, P.default_binding(), None, dev)
+    x = S.rand_c(1005, 1 << lgN)
+    ref = np.fft.fft(x)
+    Xl = f.forward(torch.from_numpy(f.scatter_time(x)).to(dev))
+    torch.cuda.synchronize()
+    want = ref[f.freq_index()]
+    assert S.nre(Xl.cpu().numpy(), want) <= S.tol(1 << lgN)
+    back = f.inverse(Xl)
+    torch.cuda.synchronize()
+    assert S.nre(back.cpu().numpy().reshape(-1), x.reshape(f.N1, f.N2).reshape(-1)) <= S.tol(1 << lgN)
