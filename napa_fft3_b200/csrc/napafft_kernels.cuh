@@ -451,7 +451,7 @@ struct TileCtx {
     int ra;                          // outer index of the tile (twiddle exponent of distributed passes)
 };
 template <int LOG2L, int MAP>
-__device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long tile) {
+__device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long tile, const unsigned flags) {
     constexpr int C = 1 << plan_log2c(LOG2L);
     TileCtx c;
     lane_ids<LOG2L, MAP>(threadIdx.x, c.t, c.q);
@@ -461,7 +461,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
     c.item = b;
     c.s_xoff = (long long)ra * p.s_SA + (long long)rg * p.s_SG;
     c.d_xoff = (long long)ra * p.d_SA + (long long)rg * p.d_SG;
-    if (p.flags & PF_Q_IS_BATCH) {
+    if (flags & PF_Q_IS_BATCH) {
         c.item = b * C + c.q;
     } else {
         c.s_xoff += c.q * p.s_q;
@@ -480,7 +480,9 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 // All 16 data loads of a thread are issued back to back into v[], and every optional fusion is a
 // separate warp-uniform branch over the whole register array, so unused fusions cost nothing and
 // used ones do not serialise the loads.
-template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook>
+// ALLOWED: the flag bits this instantiation can ever see (the persistent pipeline knows the role of
+// each pass at compile time; masking lets the compiler drop the other fusion paths = smaller code).
+template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook, unsigned ALLOWED = 0xffffffffu>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
                                          const long long src_item_delta, const long long dst_item_delta,
                                          const L2Policies &pol, Hook &hook) {
@@ -490,8 +492,8 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     constexpr bool REORDER_OK = LOG2L >= 7 && plan_nstages(LOG2L) > 1;   // swizzled reorder buffer
     static_assert(plan_nstages(LOG2L) > 1 || LM == SM_, "single-stage tiles cannot switch lane maps");
     const int src_hint = p.src_hint, dst_hint = p.dst_hint;
-    const unsigned flags = p.flags;
-    const TileCtx c = tile_ctx<LOG2L, LM>(p, tile);
+    const unsigned flags = p.flags & ALLOWED;
+    const TileCtx c = tile_ctx<LOG2L, LM>(p, tile, flags);
     const int t = c.t, q = c.q;
     const long long s_xoff = c.s_xoff;
     // a bit-reversed access on a row side goes through shared memory so that global memory sees
@@ -578,7 +580,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     }
     if (c.valid && (flags & PF_TW_LOAD)) apply_big_twiddle<T>(v, p, t, c.col, c.ra);
 
-    const TileCtx d = tile_ctx<LOG2L, SM_>(p, tile);
+    const TileCtx d = tile_ctx<LOG2L, SM_>(p, tile, flags);
     if constexpr (REORDER_OK && LM == MAP_T) {
         if (in_reorder) Stages<LOG2L, 0, 0, PLANAR, true, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
         else Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
@@ -626,7 +628,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 template <int LOG2L, int LM>
 __device__ __forceinline__ void tile_l2_prefetch(const PassParams &p, const long long tile) {
     constexpr int T = (1 << LOG2L) / 16;
-    const TileCtx c = tile_ctx<LOG2L, LM>(p, tile);
+    const TileCtx c = tile_ctx<LOG2L, LM>(p, tile, p.flags);
     if (!c.valid) return;
     const cplx *src = p.src + c.item * p.src_batch_stride + c.s_xoff;
 #pragma unroll
@@ -753,6 +755,15 @@ __device__ __forceinline__ void pipe_wait(const PipeWork &w, int *error) {
 // PK: 0 = natural order   (A column-like (Q,Q) into the ring, B row-like load + transposed store (T,Q))
 //     1 = forward, bit-reversed output (A column-like, B row-like (T,T))
 //     2 = inverse, bit-reversed input  (A row-like (T,T), B column-like)
+// flag bits each pass of a pipeline kind can carry (see exec_c2c)
+__host__ __device__ constexpr unsigned pipe_flags_a(int pk) {
+    return pk == 0 ? (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_WIN_REV | PF_CONJ_IN | PF_TW_STORE | PF_RIFFT_PRE)
+         : pk == 1 ? (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_TW_STORE | PF_OUT_REV)
+                   : (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_CONJ_IN | PF_IN_REV);
+}
+__host__ __device__ constexpr unsigned pipe_flags_b(int pk) {
+    return pk == 0 ? PF_CONJ_OUT : pk == 1 ? PF_OUT_REV : (PF_IN_REV | PF_TW_LOAD | PF_CONJ_OUT);
+}
 __host__ __device__ constexpr int pipe_kind_a(int pk) { return pk == 2 ? 1 : 0; }
 __host__ __device__ constexpr int pipe_kind_b(int pk) { return pk == 0 ? 2 : (pk == 1 ? 1 : 0); }
 
@@ -839,8 +850,8 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipel
         for (int j = 0; j < group; j++) {
             if (j) __syncthreads();            // previous tile of the group is done with sm
             PipeHook hook{p, &st, k, j == group - 1};
-            if (is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false>(p.a, tile + j, sm, 0, p.a_dst_is_ring ? delta : 0, pol, hook);
-            else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false>(p.b, tile + j, sm, p.b_src_is_ring ? delta : 0, 0, pol, hook);
+            if (is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, PipeHook, pipe_flags_a(PK)>(p.a, tile + j, sm, 0, p.a_dst_is_ring ? delta : 0, pol, hook);
+            else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, PipeHook, pipe_flags_b(PK)>(p.b, tile + j, sm, p.b_src_is_ring ? delta : 0, 0, pol, hook);
         }
         if (threadIdx.x == 0) st.pending = p.done + (cw->is_a ? 0 : p.nchunks) + cw->chunk;
     }
