@@ -73,11 +73,11 @@ struct State {
     void *pinned[2] = {}; size_t pinned_bytes = 0;
     void *dbuf[2] = {}; size_t dbuf_bytes = 0;
     void *dwin = nullptr; size_t dwin_bytes = 0;
-    size_t chunk_bytes = 32u << 20;       // per-launch chunk of the multi-launch fallback path
+    size_t chunk_bytes = (size_t)1 << 30; // items per launch of the multi-launch path (also the natural-order scratch size)
     size_t pipe_chunk_bytes = 32u << 20;  // chunk of the persistent pipeline (measured fastest; 4-8 MiB keeps the ring in L2 but runs slower)
     int pipe_lag = 0;                     // phases between the two passes of a chunk (0 = auto)
     int pipe_slots = 0;                   // scratch ring slots (0 = auto)
-    bool use_pipeline = true;
+    bool use_pipeline = false;            // persistent L2 pipeline: measured slower than two plain launches
     bool attrs_set = false;
     int num_sms = 148;
     std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream ticket/done block
@@ -926,7 +926,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
     if (const char *env = getenv("NAPAFFT_PIPE_SLOTS")) G.pipe_slots = atoi(env);
-    if (const char *env = getenv("NAPAFFT_NO_PIPELINE")) G.use_pipeline = atoi(env) == 0;
+    if (const char *env = getenv("NAPAFFT_PIPELINE")) G.use_pipeline = atoi(env) != 0;
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;

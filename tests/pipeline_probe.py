@@ -1,0 +1,34 @@
+"""Runs two-digit transforms through the optional persistent L2 pipeline (NAPAFFT_PIPELINE=1 is read
+at library init, hence a separate process).  argv[1]: "emul" (CPU emulation build) or "gpu"."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+import numpy as np
+import parity_suite as S
+from oracle import napa_oracle as O
+
+if sys.argv[1] == "emul":
+    from emul.build_emul import build
+    from napa_fft3_b200 import Binding, NapaFFT
+    b = Binding(build()); b.init(0)
+    napa = NapaFFT(b)
+    sizes, batch = (14, 16), 5
+else:
+    import napa_fft3_b200 as P
+    P.default_binding()
+    napa = P._default
+    sizes, batch = (14, 16, 20, 22), 9
+for lg in sizes:
+    n = 1 << lg
+    for io in (True, False):
+        S.check_fft(napa, n, io, "sqrt", "real")
+        S.check_ifft(napa, n, io, True, "complex")
+    x = np.stack([S.rand_c(i, n) for i in range(batch)])
+    for io in (True, False):
+        got = napa.fft_batch(x.copy(), in_order=io)
+        assert max(S.nre(got[i], O.fft(x[i], in_order=io)) for i in range(batch)) <= S.tol(n)
+        back = napa.fft_batch(got, direction=-1, in_order=io, scale=True)
+        assert S.nre(back, x) <= S.tol(n)
+print("pipeline ok")

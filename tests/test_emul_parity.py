@@ -115,3 +115,13 @@ def test_persistent_single_pass(napa, n, batch):
         assert S.nre(got[i], want) <= S.tol(n)
         assert S.nre(back[i], O.ifft(want.copy(), in_order=False, scale="sqrt")) <= S.tol(n)
     assert S.nre(back, x * w) < 1e-13
+
+
+def test_optional_l2_pipeline_path():
+    """the persistent two-pass pipeline (off by default, NAPAFFT_PIPELINE=1) stays correct:
+    several chunks, ring-slot reuse, natural and bit-reversed pipelines"""
+    import subprocess
+    env = dict(os.environ, NAPAFFT_PIPELINE="1", NAPAFFT_PIPE_CHUNK_KB="256")
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -186,3 +186,12 @@ def test_distributed_building_blocks_single_rank(napa, lgN):
     back = f.inverse(Xl)
     torch.cuda.synchronize()
     assert S.nre(back.cpu().numpy().reshape(-1), x.reshape(f.N1, f.N2).reshape(-1)) <= S.tol(1 << lgN)
+
+
+def test_optional_l2_pipeline_path_gpu():
+    import subprocess
+    for extra in ({}, {"NAPAFFT_PIPE_CHUNK_KB": "4096"}):
+        env = dict(os.environ, NAPAFFT_PIPELINE="1", **extra)
+        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "gpu"],
+                             env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
