@@ -342,9 +342,17 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
 // ------------------------------------------------------------------------------------------
 // planner
 // ------------------------------------------------------------------------------------------
-static std::vector<int> digits_of(int lg) {
+static std::vector<int> digits_of(int lg, bool natural = false) {
     if (lg <= 13) return { lg };
-    if (lg <= 23) { int l1 = std::min(10, lg / 2); return { l1, lg - l1 }; }
+    if (lg <= 23) {
+        // column digit first.  2^8 columns = 128-byte segments on 2048-point tiles (the most efficient
+        // column tile); the row digit takes the rest as long as it stays <= 2^12.
+        // Natural order also stores transposed C*16-byte segments in the row pass, so it balances the
+        // digits sooner (measured on B200: tools/sweep_sizes.py with NAPAFFT_COL_DIGIT).
+        int l1 = lg <= 15 ? 7 : (natural ? (lg <= 19 ? 8 : (lg == 20 ? 9 : 10)) : (lg <= 20 ? 8 : std::min(10, lg - 12)));
+        if (const char *env = getenv("NAPAFFT_COL_DIGIT")) { int v = atoi(env); if (v >= 4 && v <= 10 && lg - v >= 4 && lg - v <= 13) l1 = v; }
+        return { l1, lg - l1 };
+    }
     int l1 = std::min(10, lg / 3), l2 = std::min(10, (lg - l1) / 2);
     return { l1, l2, lg - l1 - l2 };
 }
@@ -430,7 +438,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         return NAPA_OK;
     }
 
-    std::vector<int> d = digits_of(lg);
+    std::vector<int> d = digits_of(lg, o.in_order != 0);
     const int p = (int)d.size();
 
     if (p == 1) {
