@@ -197,24 +197,25 @@ static int ensure_scratch(size_t bytes) {
 // tile kinds (lane maps): 0 column-like, 1 row-like, 2 row-like load + transposed store
 enum { KIND_COL = 0, KIND_ROW = 1, KIND_ROWT = 2 };
 typedef void (*pass_fn)(const PassParams);
-template <int K> static pass_fn pass_kernel_k(int l) {
+template <int K, bool LEAN> static pass_fn pass_kernel_k(int l) {
     switch (l) {
-    case 4: return napa::fft_pass_kernel<4, K>;
-    case 5: return napa::fft_pass_kernel<5, K>;
-    case 6: return napa::fft_pass_kernel<6, K>;
-    case 7: return napa::fft_pass_kernel<7, K>;
-    case 8: return napa::fft_pass_kernel<8, K>;
-    case 9: return napa::fft_pass_kernel<9, K>;
-    case 10: return napa::fft_pass_kernel<10, K>;
-    case 11: return napa::fft_pass_kernel<11, K>;
-    case 12: return napa::fft_pass_kernel<12, K>;
-    case 13: return napa::fft_pass_kernel<13, K>;
+    case 4: return napa::fft_pass_kernel<4, K, LEAN>;
+    case 5: return napa::fft_pass_kernel<5, K, LEAN>;
+    case 6: return napa::fft_pass_kernel<6, K, LEAN>;
+    case 7: return napa::fft_pass_kernel<7, K, LEAN>;
+    case 8: return napa::fft_pass_kernel<8, K, LEAN>;
+    case 9: return napa::fft_pass_kernel<9, K, LEAN>;
+    case 10: return napa::fft_pass_kernel<10, K, LEAN>;
+    case 11: return napa::fft_pass_kernel<11, K, LEAN>;
+    case 12: return napa::fft_pass_kernel<12, K, LEAN>;
+    case 13: return napa::fft_pass_kernel<13, K, LEAN>;
     }
     return nullptr;
 }
-static pass_fn pass_kernel(int l, int kind) {
+static pass_fn pass_kernel(int l, int kind, bool lean) {
     if (l < 7) kind = KIND_COL;            // small L: one lane map (see kind_lm)
-    return kind == KIND_COL ? pass_kernel_k<0>(l) : (kind == KIND_ROW ? pass_kernel_k<1>(l) : pass_kernel_k<2>(l));
+    if (lean) return kind == KIND_COL ? pass_kernel_k<0, true>(l) : (kind == KIND_ROW ? pass_kernel_k<1, true>(l) : pass_kernel_k<2, true>(l));
+    return kind == KIND_COL ? pass_kernel_k<0, false>(l) : (kind == KIND_ROW ? pass_kernel_k<1, false>(l) : pass_kernel_k<2, false>(l));
 }
 
 static int set_kernel_attrs() {
@@ -222,8 +223,10 @@ static int set_kernel_attrs() {
     for (int l = 4; l <= 13; l++)
         for (int kind = 0; kind < 3; kind++) {
             size_t sm = napa::kind_smem_bytes(l, kind);
-            if (sm > 48 * 1024)
-                CU(cudaFuncSetAttribute((const void *)pass_kernel(l, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            if (sm > 48 * 1024) {
+                CU(cudaFuncSetAttribute((const void *)pass_kernel(l, kind, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                CU(cudaFuncSetAttribute((const void *)pass_kernel(l, kind, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            }
         }
     G.attrs_set = true;
     return NAPA_OK;
@@ -235,7 +238,7 @@ static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStr
     p.lg_tpi = ilog2((size_t)p.tiles_per_item); p.lg_G = ilog2((size_t)p.G);
     if (ntiles <= 0) return NAPA_OK;
     if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
-    pass_fn fn = pass_kernel(l, kind);
+    pass_fn fn = pass_kernel(l, kind, (p.flags & ~napa::LEAN_FLAGS) == 0);
     NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::kind_smem_bytes(l, l < 7 ? 0 : kind), st, p);
     g_launches++;
     return NAPA_OK;

@@ -221,6 +221,7 @@ __device__ __forceinline__ unsigned long long pick_policy(const L2Policies &pol,
 // COHERENT: L2-only (.cg) because another SM may have written the line earlier in this launch
 template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, int hint, const L2Policies &pol) {
     cplx v;
+    if (!COHERENT && hint < 0) return *p;              // un-hinted launch: plain load, no policy operand
     const unsigned long long policy = pick_policy(pol, hint);
     if (COHERENT)
         asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy) : "memory");
@@ -229,6 +230,7 @@ template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, 
     return v;
 }
 __device__ __forceinline__ void st_data(cplx *p, cplx v, int hint, const L2Policies &pol) {
+    if (hint < 0) { *p = v; return; }                   // un-hinted launch: plain store
     const unsigned long long policy = pick_policy(pol, hint);
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
 }
@@ -482,7 +484,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 // used ones do not serialise the loads.
 // ALLOWED: the flag bits this instantiation can ever see (the persistent pipeline knows the role of
 // each pass at compile time; masking lets the compiler drop the other fusion paths = smaller code).
-template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook, unsigned ALLOWED = 0xffffffffu>
+template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook, unsigned ALLOWED = 0xffffffffu, bool HINTED = true>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
                                          const long long src_item_delta, const long long dst_item_delta,
                                          const L2Policies &pol, Hook &hook) {
@@ -491,7 +493,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     constexpr bool PLANAR = !(LM == MAP_Q && SM_ == MAP_Q);
     constexpr bool REORDER_OK = LOG2L >= 7 && plan_nstages(LOG2L) > 1;   // swizzled reorder buffer
     static_assert(plan_nstages(LOG2L) > 1 || LM == SM_, "single-stage tiles cannot switch lane maps");
-    const int src_hint = p.src_hint, dst_hint = p.dst_hint;
+    const int src_hint = HINTED ? p.src_hint : -1, dst_hint = HINTED ? p.dst_hint : -1;
     const unsigned flags = p.flags & ALLOWED;
     const TileCtx c = tile_ctx<LOG2L, LM>(p, tile, flags);
     const int t = c.t, q = c.q;
@@ -646,14 +648,18 @@ __host__ __device__ constexpr size_t kind_smem_bytes(int l, int kind) {
     return (kind_lm(l, kind) == MAP_Q && kind_sm(l, kind) == MAP_Q) ? plan_smem_bytes(l) : plan_smem_bytes_planar(l);
 }
 
-// One tile per CTA (single-pass transforms, and the multi-launch fallback of multi-pass ones).
-template <int LOG2L, int KIND>
+// One tile per CTA (single-pass transforms and every pass of multi-pass ones by default).
+// LEAN: compiled without the window / rifft fusion paths (most launches: every non-first pass and
+// un-windowed first passes) -- smaller code, fewer flag tests.
+constexpr unsigned LEAN_FLAGS = PF_Q_IS_BATCH | PF_IN_REV | PF_OUT_REV | PF_CONJ_IN | PF_CONJ_OUT | PF_TW_LOAD | PF_TW_STORE | PF_SCALE;
+template <int LOG2L, int KIND, bool LEAN>
 __global__ void __launch_bounds__(plan_threads(LOG2L), plan_min_ctas(LOG2L))
 fft_pass_kernel(const PassParams p) {
     NAPA_DYN_SMEM(cplx, sm);
-    const L2Policies pol = make_policies();          // created once per thread, at kernel entry
+    L2Policies pol{};                                 // plain loads/stores: no L2 policy operands
     NoHook nh;
-    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND), SyncAll, false>(p, (long long)blockIdx.x, sm, 0, 0, pol, nh);
+    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND), SyncAll, false, NoHook, LEAN ? LEAN_FLAGS : 0xffffffffu, false>(
+        p, (long long)blockIdx.x, sm, 0, 0, pol, nh);
 }
 
 // ------------------------------------------------------------------------------------------
