@@ -67,18 +67,23 @@ def cpu_oracle_step(wl, items, threads, state):
     data, win = state["data"], state["win"]
 
     def work(lo, hi):
-        for i in range(lo, hi):
-            if wl == "c1":
-                O.fft(data[i].copy())
-            elif wl == "c2":
-                y = O.fft(data[i].copy(), window=win)
-                O.ifft(y, dst=y, scale=True)
-            elif wl == "c3":
-                y = O.fft(data[i].copy(), in_order=False)
-                O.ifft(y, dst=y, in_order=False, scale=True, window=win)
-            else:
-                y = O.rfft(data[i])
-                O.rifft(y)
+        if wl == "c4":
+            for i in range(lo, hi):
+                O.rifft(O.rfft(data[i]))
+            return
+        buf = state["work"][lo:hi]
+        np.copyto(buf, data[lo:hi])
+        if wl == "c1":
+            O.c2c_batch(buf, n, 1)
+        elif wl == "c2":
+            O.c2c_batch(buf, n, 1, True, None, win)
+            O.c2c_batch(buf, n, -1, True, True)
+        else:
+            O.c2c_batch(buf, n, 1, False)
+            O.c2c_batch(buf, n, -1, False, True, win)
+    threads = max(1, min(threads, items))
+    if threads == 1:
+        return work(0, items)                  # no thread spawn around a microsecond-scale step (c1)
     per = (items + threads - 1) // threads
     ts = [threading.Thread(target=work, args=(t * per, min(items, (t + 1) * per))) for t in range(threads)]
     for t in ts:
@@ -99,7 +104,7 @@ def cpu_oracle_state(wl, items):
     else:
         data = rng.uniform(-1, 1, (items, n)) + 1j * rng.uniform(-1, 1, (items, n))
         win = O.window_vector("hann", n) if wl == "c2" else (O.fft(data[0], in_order=False) if wl == "c3" else None)
-    return {"data": data, "win": win}
+    return {"data": data, "win": win, "work": np.empty_like(data)}
 
 
 def run_reference_arm(args):
@@ -327,14 +332,16 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = algorithmic_bytes_per_step(wl) / (ms_per_step * 1e-3) / 1e9
+    launches_per_step = launches / max(args.steps, 1)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(wl)
+        # measured DRAM bytes of one whole step (sum over its launches, ncu --set full), per launch like `achieved`
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(wl)
+        traffic = float(t["dram_bytes_per_step"]) / max(launches_per_step, 1)
     except Exception:
         pass
-    launches_per_step = launches / max(args.steps, 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "napa::fft_pass_kernel<LOG2L>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "napa::fft_pass_kernel<LOG2L,KIND,LEAN> (one launch per digit pass; two per 2^14..2^20 transform)",
                 "algorithmic_bytes_per_launch": algorithmic_bytes_per_step(wl) / max(launches_per_step, 1),
                 "avg_launch_ms": ms_per_step / max(launches_per_step, 1),
                 "frac_of_nominal_8000": achieved / 8000.0}

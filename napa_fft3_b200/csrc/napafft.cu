@@ -347,17 +347,38 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
 // ------------------------------------------------------------------------------------------
 static std::vector<int> digits_of(int lg, bool natural = false) {
     if (lg <= 13) return { lg };
-    if (lg <= 23) {
-        // column digit first.  2^8 columns = 128-byte segments on 2048-point tiles (the most efficient
-        // column tile); the row digit takes the rest as long as it stays <= 2^12.
-        // Natural order also stores transposed C*16-byte segments in the row pass, so it balances the
-        // digits sooner (measured on B200: tools/sweep_sizes.py with NAPAFFT_COL_DIGIT).
-        int l1 = lg <= 15 ? 7 : (natural ? (lg <= 19 ? 8 : (lg == 20 ? 9 : 10)) : (lg <= 20 ? 8 : std::min(10, lg - 12)));
-        if (const char *env = getenv("NAPAFFT_COL_DIGIT")) { int v = atoi(env); if (v >= 4 && v <= 10 && lg - v >= 4 && lg - v <= 13) l1 = v; }
-        return { l1, lg - l1 };
+    if (const char *env = getenv("NAPAFFT_DIGITS")) {       // tuning override: "8,12" or "7,7,8" (column digits first)
+        std::vector<int> v; int sum = 0; bool ok = true;
+        for (const char *c = env; *c;) { int x = atoi(c); v.push_back(x); sum += x; while (*c && *c != ',') c++; if (*c) c++; }
+        for (size_t i = 0; i < v.size(); i++) {
+            ok = ok && v[i] >= 4 && v[i] <= (i + 1 < v.size() ? 10 : 13);
+            int rest = 0;
+            for (size_t j = i + 1; j < v.size(); j++) rest += v[j];
+            if (ok && i + 1 < v.size()) ok = rest >= napa::plan_log2c(v[i]);     // a column tile spans C contiguous columns
+        }
+        if (ok && sum == lg && v.size() >= 2 && v.size() <= 3) return v;
     }
-    int l1 = std::min(10, lg / 3), l2 = std::min(10, (lg - l1) / 2);
-    return { l1, l2, lg - l1 - l2 };
+    // Measured on B200 with tools/sweep_digits.py (profiles/r01_sweep_digits.txt).  Column digits first.
+    // Two passes while both sides keep >= 64..128-byte contiguous segments; the natural-order row pass
+    // stores C*16-byte transposed segments (C = rows per tile), so it leaves the two-digit plans
+    // sooner than the bit-reversed layouts, whose last pass is fully contiguous.  Three-digit plans
+    // run every pass at copy speed (~1/3 of the roofline); larger digits go last.
+    // The plans of both output orders coincide up to 2^18 and from 2^23.
+    switch (lg) {
+    case 14: return { 6, 8 };
+    case 15: return { 7, 8 };
+    case 16: return { 8, 8 };
+    case 17: return { 8, 9 };
+    case 18: return { 8, 10 };
+    case 19: return natural ? std::vector<int>{ 9, 10 } : std::vector<int>{ 8, 11 };
+    case 20: return natural ? std::vector<int>{ 9, 11 } : std::vector<int>{ 8, 12 };
+    case 21: return natural ? std::vector<int>{ 6, 7, 8 } : std::vector<int>{ 9, 12 };
+    case 22: return natural ? std::vector<int>{ 7, 7, 8 } : std::vector<int>{ 10, 12 };
+    }
+    const int base = lg / 3, rem = lg % 3;
+    int l1 = base, l2 = base + (rem >= 2), l3 = base + (rem >= 1);
+    if (l2 > 10) { l3 += l2 - 10; l2 = 10; }          // 2^31, 2^32: column digits stay <= 2^10
+    return { l1, l2, l3 };
 }
 
 // interface.lisp:41-48
@@ -442,6 +463,11 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     }
 
     std::vector<int> d = digits_of(lg, o.in_order != 0);
+    if (G.use_pipeline && !getenv("NAPAFFT_DIGITS")) {
+        // the optional L2 pipeline is instantiated for digit pairs sharing one tile shape
+        static const int pipe_l1[] = { 7, 7, 8, 0, 9, 9, 10, 10, 10 };     // lg = 14 .. 22
+        if (lg >= 14 && lg <= 22 && pipe_l1[lg - 14]) d = { pipe_l1[lg - 14], lg - pipe_l1[lg - 14] };
+    }
     const int p = (int)d.size();
 
     if (p == 1) {
@@ -526,42 +552,55 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         CU(cudaGetLastError());
         return NAPA_OK;
     }
-    if (natural && p == 2) {
-        // natural in -> natural out: column pass into L2-resident scratch, row pass stores transposed
+    if (natural) {
+        // natural in -> natural out, one HBM pass per digit and no separate bit-reversal pass:
+        //   p == 2: column pass src -> scratch [k1][n2], row pass scratch -> dst stored transposed (k1 + L1 k2)
+        //   p == 3: column pass src -> dst [k1][n2][n3]; column pass dst -> scratch [k2][k1][n3]; row pass
+        //           scratch -> dst stored transposed ((k1 + L1 k2) + L1 L2 k3)
+        // The inverse runs the same forward structure between conjugations (bitwise the DIT result of
+        // the bit-reversed input up to the order of additions; window index = rev(k), set by win_rev).
         OK(ensure_scratch(chunk * n * sizeof(cplx)));
-        BigTw bt; OK(ensure_big_tw(lg, &bt));
-        const long long L1 = 1LL << d[0], L2 = 1LL << d[1];
         for (size_t b0 = 0; b0 < batch; b0 += chunk) {
             const size_t nb = std::min(chunk, batch - b0);
-            PassParams p1{}; long long tpi;
-            pass_geometry(d, 0, p1, &tpi);
-            p1.src = src + b0 * sstride; p1.dst = G.scratch;
-            p1.src_batch_stride = (long long)sstride; p1.dst_batch_stride = (long long)n; p1.batch = (long long)nb;
-            p1.flags = napa::PF_TW_STORE | (inv ? napa::PF_CONJ_IN : 0);
-            p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << lg) - 1;
-            first_pass_fusions(p1, o, n, win_rev);
-            if (o.wpb) p1.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
-            OK(launch_pass(d[0], KIND_COL, p1, tpi * (long long)nb, st));
+            long long tpi;
+            const cplx *cur = src + b0 * sstride;
+            long long cur_stride = (long long)sstride;
+            for (int s = 0; s + 1 < p; s++) {
+                int lgB = 0;
+                for (int i = s + 1; i < p; i++) lgB += d[i];
+                PassParams p1{};
+                pass_geometry(d, s, p1, &tpi);
+                const bool to_scratch = s == p - 2;
+                p1.src = cur; p1.dst = to_scratch ? G.scratch : dst + b0 * dstride;
+                p1.src_batch_stride = cur_stride; p1.dst_batch_stride = (long long)(to_scratch ? n : dstride); p1.batch = (long long)nb;
+                BigTw bt; OK(ensure_big_tw(d[s] + lgB, &bt));
+                p1.flags = napa::PF_TW_STORE | ((inv && s == 0) ? napa::PF_CONJ_IN : 0);
+                p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << (d[s] + lgB)) - 1;
+                if (s == 0) {
+                    first_pass_fusions(p1, o, n, win_rev);
+                    if (o.wpb && o.wtype) p1.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
+                }
+                if (s == 1) {
+                    // a = k1 (stride L3 in scratch), output k2 at stride L1*L3: swaps the two leading digits
+                    p1.d_SA = 1LL << d[2]; p1.d_i = (1LL << d[0]) << d[2];
+                }
+                OK(launch_pass(d[s], KIND_COL, p1, tpi * (long long)nb, st));
+                cur = p1.dst; cur_stride = p1.dst_batch_stride;
+            }
             PassParams p2{};
-            pass_geometry(d, 1, p2, &tpi);
+            pass_geometry(d, p - 1, p2, &tpi);
             p2.src = G.scratch; p2.dst = dst + b0 * dstride;
             p2.src_batch_stride = (long long)n; p2.dst_batch_stride = (long long)dstride; p2.batch = (long long)nb;
             p2.flags = inv ? napa::PF_CONJ_OUT : 0;
-            // row k1 = ra*C + q, output k2 -> address k1 + L1*k2
-            p2.d_SA = 1LL << napa::plan_log2c(d[1]); p2.d_SG = 0; p2.d_i = L1; p2.d_q = 1;
-            (void)L2;
-            OK(launch_pass(d[1], KIND_ROWT, p2, tpi * (long long)nb, st));
+            // row r = ra*C + q holds the leading output digits (k1 + L1 k2); output k_last -> address r + (n / L_last) * k_last
+            p2.d_SA = 1LL << napa::plan_log2c(d[p - 1]); p2.d_SG = 0; p2.d_i = (long long)(n >> d[p - 1]); p2.d_q = 1;
+            OK(launch_pass(d[p - 1], KIND_ROWT, p2, tpi * (long long)nb, st));
         }
         CU(cudaGetLastError());
         return NAPA_OK;
     }
 
     // bit-reversed pipelines (in place on dst after the first pass), any number of digits
-    if (natural && inv) {
-        // reference order: bit-reverse first, then DIT (easy-interface.lisp:83-95)
-        OK(exec_bitrev(src, dst, n, batch, sstride, dstride, NAPA_ELT_COMPLEX, st));
-        src = dst; sstride = dstride;
-    }
     for (size_t b0 = 0; b0 < batch; b0 += chunk) {
         const size_t nb = std::min(chunk, batch - b0);
         for (int step = 0; step < p; step++) {
@@ -591,7 +630,6 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             OK(launch_pass(d[s], lgB > 0 ? KIND_COL : KIND_ROW, pp, tpi * (long long)nb, st));
         }
     }
-    if (natural && !inv) OK(exec_bitrev(dst, dst, n, batch, dstride, dstride, NAPA_ELT_COMPLEX, st));
     CU(cudaGetLastError());
     return NAPA_OK;
 }

@@ -125,3 +125,15 @@ def test_optional_l2_pipeline_path():
     out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("digits,n", [("5,5,6", 1 << 16), ("7,8", 1 << 15), ("6,5,6", 1 << 17)])
+def test_three_digit_plans(napa, digits, n, monkeypatch):
+    """the plans of 2^24 and beyond (three digit passes; natural order without a bit-reversal pass)
+    at emulator-sized n, selected with the NAPAFFT_DIGITS tuning override"""
+    monkeypatch.setenv("NAPAFFT_DIGITS", digits)
+    for in_order in (True, False):
+        S.check_fft(napa, n, in_order, "sqrt", "real")
+        S.check_ifft(napa, n, in_order, True, "complex")
+    S.check_layout_bit_exact(napa, n)
+    S.check_offsets_exact(napa, n)

@@ -16,7 +16,11 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum',
         'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_srcunit_tex_op_write.sum',
-        'lts__t_sectors_srcunit_tex_lookup_miss.sum', 'sm__cycles_elapsed.max']
+        'lts__t_sectors_srcunit_tex_lookup_miss.sum', 'sm__cycles_elapsed.max',
+        'smsp__thread_inst_executed.sum', 'sm__inst_executed_pipe_fp64.sum', 'smsp__inst_executed_pipe_fp64.sum',
+        'sm__inst_executed_pipe_lsu.sum', 'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_fma.sum',
+        'sm__inst_executed_pipe_uniform.sum', 'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_cbu.sum',
+        'sm__inst_executed_pipe_adu.sum']
 
 
 def page(rep, name):
@@ -60,6 +64,16 @@ def main():
         if 'BAR.SYNC' in r[iSrc]:
             region += 1
     print('   samples by region between barriers:', {k: '%.1f%% (%d instr)' % (100 * v / tot, cnt[k]) for k, v in acc.items()})
+    ie = [h for h in hdr if h.endswith('Instructions Executed') and 'Thread' not in h]
+    if ie:
+        iE = hdr.index(ie[0])
+        mix = collections.Counter()
+        for r in d:
+            parts = r[iSrc].split()
+            op = parts[1] if parts and parts[0].startswith('@') and len(parts) > 1 else (parts[0] if parts else '?')
+            mix[op.split('.')[0]] += int(r[iE] or 0)
+        tote = sum(mix.values()) or 1
+        print('   dynamic warp-instruction mix (%d executed):' % tote, ', '.join('%s %.1f%%' % (k, 100 * v / tote) for k, v in mix.most_common(18)))
     stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
     agg = {s: sum(int(r[hdr.index(s)]) for r in d) for s in stalls}
     print('   stall samples:', {s: v for s, v in sorted(agg.items(), key=lambda x: -x[1])[:8]})
