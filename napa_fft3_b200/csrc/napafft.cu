@@ -74,9 +74,8 @@ struct State {
     void *dbuf[2] = {}; size_t dbuf_bytes = 0;
     void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = (size_t)1 << 30; // items per launch of the multi-launch path (also the natural-order scratch size)
-    size_t pipe_chunk_bytes = 32u << 20;  // chunk of the persistent pipeline (measured fastest; 4-8 MiB keeps the ring in L2 but runs slower)
-    int pipe_lag = 0;                     // phases between the two passes of a chunk (0 = auto)
-    int pipe_slots = 0;                   // scratch ring slots (0 = auto)
+    size_t pipe_l2_bytes = 40u << 20;     // live intermediate of the group-fused kernel (groups * n * 16 B)
+    int pipe_gsize = 0;                   // CTAs per group (0 = auto)
     bool use_pipeline = false;            // persistent L2 pipeline: measured slower than two plain launches
     bool attrs_set = false;
     int num_sms = 148;
@@ -296,27 +295,25 @@ static int pipeline_resident(int la, int lb, int pk, long long *out) {
     return NAPA_OK;
 }
 
-// Chunking of the persistent pipeline.  With W resident CTAs and T tickets per chunk and pass,
-// tickets run  A(c) | A(c+1) B(c+1-lag) | ...  A tile of B(c) must not be drawn while A(c) tiles
-// are still in flight, and (scratch ring) an A(c) tile must not be drawn while B(c - slots) still
-// drains the slot: both ticket distances, 2T*lag and 2T*(slots - lag - 1), are kept >= 1.5 W.
-// Chunks are small (default 4 MiB) so that the ring (slots chunks, about 2.5 * W tiles) stays in L2.
-static void pipeline_shape(long long W, size_t n, size_t batch, int lg_tile_pts, bool ring, napa::PipeParams &pp) {
-    size_t pchunk = std::max<size_t>(1, G.pipe_chunk_bytes / (n * sizeof(cplx)));
-    pchunk = std::min(pchunk, batch);
-    const long long T = (long long)pchunk * (long long)(n >> lg_tile_pts);
-    long long k = (3 * W / 2 + 2 * T - 1) / (2 * T);
-    if (k < 1) k = 1;
-    pp.items = (long long)batch; pp.chunk = (int)pchunk; pp.nchunks = (int)((batch + pchunk - 1) / pchunk);
-    pp.lag = G.pipe_lag > 0 ? G.pipe_lag : (int)k;
-    pp.slots = ring ? (G.pipe_slots > 0 ? G.pipe_slots : pp.lag + 1 + (int)k) : 0;
-    pp.group = 1;
-    pp.tiles_per_item = (long long)(n >> lg_tile_pts);
+// Shape of the group-fused launch.  W = co-resident CTAs, T = tiles per transform and pass.  The
+// live intermediate is ngroups * n * 16 bytes: ngroups is capped so that it stays within
+// G.pipe_l2_bytes (a fraction of the 126 MB L2), and a group is never wider than T CTAs.
+static void pipeline_shape(long long W, size_t n, size_t batch, long long T, napa::PipeParams &pp) {
+    long long ng = std::max<long long>(1, (long long)(G.pipe_l2_bytes / (n * sizeof(cplx))));
+    ng = std::min<long long>(ng, (long long)batch);
+    long long gs = std::min<long long>(T, std::max<long long>(1, W / ng));
+    if (G.pipe_gsize > 0) gs = std::min<long long>(std::min<long long>(G.pipe_gsize, T), W);
+    ng = std::min<long long>(std::max<long long>(1, W / gs), (long long)batch);
+#ifdef NAPA_EMULATE
+    gs = 1; ng = std::min<long long>(3, (long long)batch);     // the emulator runs CTAs one after the other: no inter-CTA waits
+#endif
+    pp.items = (long long)batch; pp.gsize = (int)gs; pp.ngroups = (int)ng;
+    pp.tiles_a = pp.tiles_b = (int)T;
 }
 
 static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStream_t st) {
     pipe_fn fn = pipe_kernel(la, lb, pk);
-    if (!fn) return fail(NAPA_E_UNSUPPORTED, "no pipeline kernel for digits (%d, %d)", la, lb);
+    if (!fn) return fail(NAPA_E_UNSUPPORTED, "no fused kernel for digits (%d, %d)", la, lb);
     OK(ensure_stage_tw(la));
     OK(ensure_stage_tw(lb));
     pp.a.stage_tw = G.stage_tw[la];
@@ -324,20 +321,22 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     pp.a.lg_tpi = ilog2((size_t)pp.a.tiles_per_item); pp.a.lg_G = ilog2((size_t)pp.a.G);
     pp.b.lg_tpi = ilog2((size_t)pp.b.tiles_per_item); pp.b.lg_G = ilog2((size_t)pp.b.G);
     const size_t smem = std::max(napa::kind_smem_bytes(la, napa::pipe_kind_a(pk)), napa::kind_smem_bytes(lb, napa::pipe_kind_b(pk)));
-    long long W;
-    OK(pipeline_resident(la, lb, pk, &W));
-    const size_t cbytes = 16 + 2 * (size_t)pp.nchunks * sizeof(unsigned);
+    const size_t cbytes = (size_t)pp.ngroups * 32 * sizeof(unsigned);
     unsigned char *ctr;
     OK(ensure_counters(st, cbytes, &ctr));
     CU(cudaMemsetAsync(ctr, 0, cbytes, st));
-    pp.ticket = (unsigned long long *)ctr;
-    pp.done = (unsigned *)(ctr + 16);
+    pp.bar = (unsigned *)ctr;
     pp.error = G.d_error;
     if (const char *env = getenv("NAPAFFT_DEBUG")) pp.debug = atoi(env);
     if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
-    const long long total_tiles = pp.items * pp.tiles_per_item * 2;      // in tickets
-    long long grid = std::min<long long>(W, total_tiles);
-    NAPA_LAUNCH(fn, (unsigned)grid, napa::plan_threads(la), smem, st, pp);
+    const unsigned grid = (unsigned)(pp.gsize * pp.ngroups);
+#ifdef NAPA_EMULATE
+    NAPA_LAUNCH(fn, grid, napa::plan_threads(la), smem, st, pp);
+#else
+    // cooperative launch: every CTA of the grid is resident before any of them waits on another
+    void *args[] = { (void *)&pp };
+    CU(cudaLaunchCooperativeKernel((const void *)fn, dim3(grid), dim3(napa::plan_threads(la)), args, smem, st));
+#endif
     g_launches++;
     return NAPA_OK;
 }
@@ -464,7 +463,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
 
     std::vector<int> d = digits_of(lg, o.in_order != 0);
     if (G.use_pipeline && !getenv("NAPAFFT_DIGITS")) {
-        // the optional L2 pipeline is instantiated for digit pairs sharing one tile shape
+        // the group-fused kernel is instantiated for digit pairs sharing one tile shape
         static const int pipe_l1[] = { 7, 7, 8, 0, 9, 9, 10, 10, 10 };     // lg = 14 .. 22
         if (lg >= 14 && lg <= 22 && pipe_l1[lg - 14]) d = { pipe_l1[lg - 14], lg - pipe_l1[lg - 14] };
     }
@@ -499,12 +498,11 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         const int la = pk == 2 ? d[1] : d[0], lb = pk == 2 ? d[0] : d[1];
         long long W;
         OK(pipeline_resident(la, lb, pk, &W));
-        pipeline_shape(W, n, batch, napa::plan_log2pts(d[0]), natural, pp);
-        const size_t pchunk = (size_t)pp.chunk;
+        pipeline_shape(W, n, batch, (long long)(n >> napa::plan_log2pts(d[0])), pp);
         long long tpi;
         if (natural) {
-            // A: column pass src -> scratch ring (+ inter-pass twiddle); B: row pass ring -> dst, transposed store
-            OK(ensure_scratch((size_t)pp.slots * pchunk * n * sizeof(cplx)));
+            // A: column pass src -> the group's scratch slot (+ inter-pass twiddle); B: row pass slot -> dst, transposed store
+            OK(ensure_scratch((size_t)pp.ngroups * n * sizeof(cplx)));
             BigTw bt; OK(ensure_big_tw(lg, &bt));
             PassParams &p1 = pp.a, &p2 = pp.b;
             pass_geometry(d, 0, p1, &tpi);
@@ -972,9 +970,8 @@ NAPA_API int napafft_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(NAPA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
-    if (const char *env = getenv("NAPAFFT_PIPE_CHUNK_KB")) G.pipe_chunk_bytes = (size_t)atoll(env) << 10;
-    if (const char *env = getenv("NAPAFFT_PIPE_LAG")) G.pipe_lag = atoi(env);
-    if (const char *env = getenv("NAPAFFT_PIPE_SLOTS")) G.pipe_slots = atoi(env);
+    if (const char *env = getenv("NAPAFFT_PIPE_L2_MB")) G.pipe_l2_bytes = (size_t)atoll(env) << 20;
+    if (const char *env = getenv("NAPAFFT_PIPE_GSIZE")) G.pipe_gsize = atoi(env);
     if (const char *env = getenv("NAPAFFT_PIPELINE")) G.use_pipeline = atoi(env) != 0;
     G.num_sms = prop.multiProcessorCount;
     G.device = device;

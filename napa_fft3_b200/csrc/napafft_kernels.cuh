@@ -663,105 +663,29 @@ fft_pass_kernel(const PassParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent two-pass pipeline: ONE launch runs both digit passes of every transform of a batch.
-// CTAs draw tickets from a global counter; tickets are ordered in phases
-//     phase ph:  pass A of chunk ph,  then pass B of chunk ph - LAG
-// so that by the time a pass-B tile of chunk c is drawn, the pass-A tiles of chunk c were drawn
-// >= LAG chunks earlier and their output is still L2-resident.  A pass-B tile waits (acquire
-// spin by one thread) until done[A][c] == tiles(c); deadlock-free because a waiter only ever
-// waits on lower tickets, which are held by running CTAs.  With a scratch ring (natural-order
-// output) pass A of chunk c additionally waits for pass B of chunk c - SLOTS to have drained
-// the slot it is about to overwrite.  Tickets are decoded two tiles ahead by one thread so that
-// the atomic, the decode and the dependency check stay off the critical path.
+// Group-fused two-pass kernel: ONE launch runs both digit passes of every transform of a batch
+// and the intermediate never leaves L2.  The grid is `ngroups` groups of `gsize` co-resident CTAs
+// (cooperative launch).  A group owns one transform at a time: its CTAs share the pass-A tiles,
+// meet at a group barrier (one arrival counter per group, release/acquire at gpu scope), then
+// share the pass-B tiles, whose loads bypass L1 (ld.global.cg) and hit the lines pass A just
+// wrote.  The live intermediate is ngroups * n * 16 bytes, sized by the host to a fraction of L2.
+//   PK 0: natural order.  A = column digit, src -> the group's scratch slot [k1][n2]; B = row
+//         digit, slot -> dst stored transposed.  A second barrier per transform keeps the next
+//         transform's pass A from overwriting the slot while pass B still reads it.
+//   PK 1: forward, bit-reversed output.  A = column digit src -> dst, B = row digit in place.
+//   PK 2: inverse of a bit-reversed input. A = row digit src -> dst, B = column digit in place.
 // ------------------------------------------------------------------------------------------
-#ifndef NAPA_PIPE_COHERENT
-#define NAPA_PIPE_COHERENT true
-#endif
 struct PipeParams {
     PassParams a, b;                 // pass A (first executed) and pass B
     long long items;                 // batch
-    int chunk;                       // items per chunk
-    int nchunks;
-    int lag;                         // phases between pass A and pass B of a chunk
-    int slots;                       // scratch ring slots (0: intermediate lives in dst)
-    int a_dst_is_ring, b_src_is_ring;
-    long long tiles_per_item;        // TICKET units per item: one ticket = `group` adjacent tiles of one pass
-    int group;                       // tiles per ticket (bookkeeping is amortised over a group)
-    unsigned long long *ticket;      // zeroed before launch
-    unsigned *done;                  // [2][nchunks], zeroed before launch
-    int *error;                      // set to 1 if a wait timed out (never expected)
+    int gsize, ngroups;              // CTAs per group, groups (grid = gsize * ngroups)
+    int tiles_a, tiles_b;            // tiles per transform of each pass
+    int a_dst_is_ring, b_src_is_ring;// intermediate lives in scratch slot `group` (else in dst)
+    unsigned *bar;                   // [ngroups][32] arrival counters (one 128-byte line each), zeroed before launch
+    int *error;                      // set to 1 if a barrier wait timed out (never expected)
     int debug;
 };
 
-__device__ __forceinline__ long long pipe_tilesum(const PipeParams &p, long long k) {
-    // tiles of chunks [0, k)
-    long long items = k * p.chunk;
-    if (items > p.items) items = p.items;
-    return items * p.tiles_per_item;
-}
-__device__ __forceinline__ long long pipe_prefix(const PipeParams &p, long long ph) {
-    long long ka = ph < p.nchunks ? ph : p.nchunks;
-    long long kb = ph - p.lag;
-    kb = kb < 0 ? 0 : (kb < p.nchunks ? kb : p.nchunks);
-    return pipe_tilesum(p, ka) + pipe_tilesum(p, kb);
-}
-
-struct PipeWork {                    // a decoded ticket
-    long long tile;                  // global tile index, -1 = no more work
-    long long delta;                 // scratch-ring item delta
-    int chunk, is_a;
-    int ready;                       // dependencies satisfied (checked without blocking)
-    const unsigned *dep; unsigned dep_target;
-};
-
-__device__ __forceinline__ PipeWork pipe_decode(const PipeParams &p, const long long tk, const long long nphase, const long long total) {
-    PipeWork w;
-    w.tile = -1; w.delta = 0; w.chunk = 0; w.is_a = 0; w.ready = 1; w.dep = nullptr; w.dep_target = 0;
-    if (tk >= total) return w;
-    long long lo = 0, hi = nphase;                         // phase = largest ph with prefix(ph) <= tk
-    while (hi - lo > 1) {
-        const long long mid = (lo + hi) >> 1;
-        if (pipe_prefix(p, mid) <= tk) lo = mid; else hi = mid;
-    }
-    const long long ph = lo;
-    long long local = tk - pipe_prefix(p, ph);
-    const long long a_tiles = ph < p.nchunks ? pipe_tilesum(p, ph + 1) - pipe_tilesum(p, ph) : 0;
-    const bool is_a = local < a_tiles;
-    const long long c = is_a ? ph : ph - p.lag;
-    if (!is_a) local -= a_tiles;
-    const long long item0 = c * p.chunk;
-    if (is_a) {
-        if (p.slots && c >= p.slots) {
-            const long long cc = c - p.slots;
-            w.dep = p.done + p.nchunks + cc;
-            w.dep_target = (unsigned)(pipe_tilesum(p, cc + 1) - pipe_tilesum(p, cc));
-        }
-    } else {
-        w.dep = p.done + c;
-        w.dep_target = (unsigned)(pipe_tilesum(p, c + 1) - pipe_tilesum(p, c));
-    }
-    if (w.dep) { w.ready = ld_acquire_u32(w.dep) >= w.dep_target; __threadfence(); }
-    w.tile = (item0 * p.tiles_per_item + local) * p.group;     // first tile of the group
-    w.delta = p.slots ? (long long)(c % p.slots) * p.chunk - item0 : 0;
-    w.chunk = (int)c;
-    w.is_a = is_a ? 1 : 0;
-    return w;
-}
-
-__device__ __forceinline__ void pipe_wait(const PipeWork &w, int *error) {
-    if (!w.dep) return;
-    unsigned spins = 0;
-    while (ld_acquire_u32(w.dep) < w.dep_target) {
-        napa_nanosleep(64);
-        if (++spins > (1u << 24)) { *error = 1; break; }      // ~seconds: bail out instead of hanging the GPU
-    }
-    __threadfence();
-}
-
-// PK: 0 = natural order   (A column-like (Q,Q) into the ring, B row-like load + transposed store (T,Q))
-//     1 = forward, bit-reversed output (A column-like, B row-like (T,T))
-//     2 = inverse, bit-reversed input  (A row-like (T,T), B column-like)
-// flag bits each pass of a pipeline kind can carry (see exec_c2c)
 __host__ __device__ constexpr unsigned pipe_flags_a(int pk) {
     return pk == 0 ? (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_WIN_REV | PF_CONJ_IN | PF_TW_STORE | PF_RIFFT_PRE)
          : pk == 1 ? (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_TW_STORE | PF_OUT_REV)
@@ -773,95 +697,57 @@ __host__ __device__ constexpr unsigned pipe_flags_b(int pk) {
 __host__ __device__ constexpr int pipe_kind_a(int pk) { return pk == 2 ? 1 : 0; }
 __host__ __device__ constexpr int pipe_kind_b(int pk) { return pk == 0 ? 2 : (pk == 1 ? 1 : 0); }
 
-// Thread 0 does the bookkeeping from a hook that runs in the MIDDLE of a tile (right after the
-// last exchange, before the final radix stage and the stores): there it publishes the completion
-// of the PREVIOUS tile (its stores were issued a whole tile ago, so the fence is cheap), decodes
-// the ticket two tiles ahead and checks the next tile's dependencies without blocking.  Nothing
-// but one barrier separates consecutive tiles on the compute warps' critical path.
-// Bookkeeping state of one persistent CTA.  It lives in shared memory and only thread 0 touches
-// it, so it costs the compute threads no registers across the tile body.
-struct PipeState {
-    PipeWork work[3];                // ring: slot k%3 = k-th tile of this CTA
-    long long next_ticket;
-    unsigned *pending;               // completion counter of the previous tile, not yet published
-};
-
-// (measured: making this a real call is far worse -- the register save/restore around the call
-// site is paid by every thread)
-__device__ __forceinline__ void pipe_bookkeeping(const PipeParams &p, PipeState *st, const int k) {
-    if (st->pending) { __threadfence(); atomicAdd(st->pending, 1u); st->pending = nullptr; }
-    const PipeWork nxt = st->work[(k + 1) % 3];
-    PipeWork w;
-    w.tile = -1;
-    if (nxt.tile >= 0) {
-        const long long nphase = (long long)p.nchunks + p.lag;
-        w = pipe_decode(p, st->next_ticket, nphase, pipe_prefix(p, nphase));
-        if (w.tile >= 0) st->next_ticket = (long long)atomicAdd(p.ticket, 1ull);
-        if (!nxt.ready && nxt.dep && ld_acquire_u32(nxt.dep) >= nxt.dep_target) {
-            __threadfence();
-            st->work[(k + 1) % 3].ready = 1;
+// All CTAs of a group arrive; returns when `target` arrivals are visible.  Stores issued by any
+// thread of an arriving CTA before the barrier are visible to every thread of a released CTA.
+__device__ __forceinline__ void group_barrier(unsigned *ctr, const unsigned target, int *error) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned spins = 0;
+        while (ld_acquire_u32(ctr) < target) {
+            napa_nanosleep(64);
+            if (++spins > (1u << 26)) { *error = 1; break; }      // seconds: a lost CTA, never expected
         }
     }
-    st->work[(k + 2) % 3] = w;
+    __syncthreads();
 }
-
-struct PipeHook {
-    const PipeParams &p;
-    PipeState *st;
-    int k;
-    bool active;                     // only the last tile of a group does the bookkeeping
-    __device__ __forceinline__ void operator()() const {
-        if (active && threadIdx.x == 0) pipe_bookkeeping(p, st, k);
-    }
-};
 
 template <int LA, int LB, int PK>
 __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
-    static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a pipeline use the same tile shape");
+    static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a fused pair use the same tile shape");
     constexpr int KA = pipe_kind_a(PK), KB = pipe_kind_b(PK);
     NAPA_DYN_SMEM(cplx, sm);
-    __shared__ PipeState st;
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
-    if (threadIdx.x == 0) {
-        const long long nphase = (long long)p.nchunks + p.lag;
-        const long long total = pipe_prefix(p, nphase);
-        PipeWork w0 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
-        PipeWork w1 = w0;
-        w1.tile = -1;
-        st.next_ticket = 0;
-        if (w0.tile >= 0) w1 = pipe_decode(p, (long long)atomicAdd(p.ticket, 1ull), nphase, total);
-        if (w1.tile >= 0) st.next_ticket = (long long)atomicAdd(p.ticket, 1ull);
-        if (w0.tile >= 0 && !w0.ready) { pipe_wait(w0, p.error); w0.ready = 1; }
-        st.work[0] = w0;
-        st.work[1] = w1;
-        st.pending = nullptr;
-    }
-    for (int k = 0;; k++) {
-        __syncthreads();                       // publishes slots k%3, (k+1)%3; previous tile is done with sm
-        const PipeWork *cw = &st.work[k % 3];
-        const long long tile = cw->tile;
-        if (tile < 0) break;
-        if (!cw->ready) {
-            // rare: dependencies were not yet satisfied at the mid-tile check.  This tile may depend
-            // on the previous tile of this very CTA, so publish that first, then block.
-            if (threadIdx.x == 0) {
-                if (st.pending) { __threadfence(); atomicAdd(st.pending, 1u); st.pending = nullptr; }
-                pipe_wait(*cw, p.error);
-            }
+    NoHook nh;
+    const int g = (int)blockIdx.x / p.gsize, r = (int)blockIdx.x - g * p.gsize;
+    unsigned *ctr = p.bar + 32 * g;
+    unsigned arrivals = 0;
+    for (long long item = g; item < p.items; item += p.ngroups) {
+        const long long delta = (long long)g - item;
+        bool first = true;
+        for (int t = r; t < p.tiles_a; t += p.gsize) {
+            if (!first) __syncthreads();       // previous tile is done with sm
+            first = false;
+            run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, pipe_flags_a(PK)>(
+                p.a, item * p.tiles_a + t, sm, 0, p.a_dst_is_ring ? delta : 0, pol, nh);
+        }
+        arrivals += (unsigned)p.gsize;
+        group_barrier(ctr, arrivals, p.error);
+        first = true;
+        for (int t = r; t < p.tiles_b; t += p.gsize) {
+            if (!first) __syncthreads();
+            first = false;
+            run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, NoHook, pipe_flags_b(PK)>(
+                p.b, item * p.tiles_b + t, sm, p.b_src_is_ring ? delta : 0, 0, pol, nh);
+        }
+        if (PK == 0) {                          // the slot is rewritten by the next transform's pass A
+            arrivals += (unsigned)p.gsize;
+            group_barrier(ctr, arrivals, p.error);
+        } else {
             __syncthreads();
         }
-        const long long delta = cw->delta;
-        const bool is_a = cw->is_a != 0;
-        const int group = p.group;
-        for (int j = 0; j < group; j++) {
-            if (j) __syncthreads();            // previous tile of the group is done with sm
-            PipeHook hook{p, &st, k, j == group - 1};
-            if (is_a) run_tile<LA, NAPA_PIPE_COHERENT, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, PipeHook, pipe_flags_a(PK)>(p.a, tile + j, sm, 0, p.a_dst_is_ring ? delta : 0, pol, hook);
-            else run_tile<LB, NAPA_PIPE_COHERENT, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, PipeHook, pipe_flags_b(PK)>(p.b, tile + j, sm, p.b_src_is_ring ? delta : 0, 0, pol, hook);
-        }
-        if (threadIdx.x == 0) st.pending = p.done + (cw->is_a ? 0 : p.nchunks) + cw->chunk;
     }
-    if (threadIdx.x == 0 && st.pending) { __threadfence(); atomicAdd(st.pending, 1u); }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-"""Runs two-digit transforms through the optional persistent L2 pipeline (NAPAFFT_PIPELINE=1 is read
+"""Runs two-digit transforms through the group-fused two-pass kernel (NAPAFFT_PIPELINE is read
 at library init, hence a separate process).  argv[1]: "emul" (CPU emulation build) or "gpu"."""
 import os
 import sys
@@ -31,4 +31,16 @@ for lg in sizes:
         assert max(S.nre(got[i], O.fft(x[i], in_order=io)) for i in range(batch)) <= S.tol(n)
         back = napa.fft_batch(got, direction=-1, in_order=io, scale=True)
         assert S.nre(back, x) <= S.tol(n)
+if sys.argv[1] != "emul":
+    # more transforms than groups: every group loops over several transforms (slot reuse, barrier epochs)
+    for lg, batch in ((14, 1500), (16, 333), (18, 70)):
+        n = 1 << lg
+        rng = np.random.Generator(np.random.Philox(lg))
+        x = rng.uniform(-1, 1, (batch, n)) + 1j * rng.uniform(-1, 1, (batch, n))
+        for io in (True, False):
+            got = napa.fft_batch(x.copy(), in_order=io)
+            for i in (0, 1, batch // 2, batch - 1):
+                assert S.nre(got[i], O.fft(x[i], in_order=io)) <= S.tol(n), (lg, io, i)
+            back = napa.fft_batch(got, direction=-1, in_order=io, scale=True)
+            assert S.nre(back, x) <= S.tol(n), (lg, io)
 print("pipeline ok")
