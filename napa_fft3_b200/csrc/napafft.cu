@@ -6,6 +6,9 @@
 #include "napafft_kernels.cuh"
 #include "../../include/napafft.h"
 
+#ifndef NAPA_EMULATE
+#include <cuda.h>          // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
+#endif
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -245,6 +248,11 @@ static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStr
 
 // persistent two-pass pipeline kernels: (first-executed digit, second digit, pipeline kind)
 typedef void (*pipe_fn)(const napa::PipeParams);
+#ifndef NAPA_EMULATE
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+#endif
 #define NAPA_PIPE_CASE(a, b)                                                    \
     if (la == a && lb == b)                                                     \
         return pk == 0 ? napa::fft_pipeline_kernel<a, b, 0> : (pk == 1 ? napa::fft_pipeline_kernel<a, b, 1> : napa::fft_pipeline_kernel<a, b, 2>);
@@ -284,7 +292,7 @@ static int pipeline_resident(int la, int lb, int pk, long long *out) {
     static std::map<pipe_fn, int> occ;
     auto it = occ.find(fn);
     if (it == occ.end()) {
-        const size_t smem = std::max(napa::kind_smem_bytes(la, napa::pipe_kind_a(pk)), napa::kind_smem_bytes(lb, napa::pipe_kind_b(pk)));
+        const size_t smem = napa::pipe_smem_bytes(la, lb, pk);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la), smem));
@@ -320,7 +328,7 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     pp.b.stage_tw = G.stage_tw[lb];
     pp.a.lg_tpi = ilog2((size_t)pp.a.tiles_per_item); pp.a.lg_G = ilog2((size_t)pp.a.G);
     pp.b.lg_tpi = ilog2((size_t)pp.b.tiles_per_item); pp.b.lg_G = ilog2((size_t)pp.b.G);
-    const size_t smem = std::max(napa::kind_smem_bytes(la, napa::pipe_kind_a(pk)), napa::kind_smem_bytes(lb, napa::pipe_kind_b(pk)));
+    const size_t smem = napa::pipe_smem_bytes(la, lb, pk);
     const size_t cbytes = (size_t)pp.ngroups * 32 * sizeof(unsigned);
     unsigned char *ctr;
     OK(ensure_counters(st, cbytes, &ctr));
@@ -330,6 +338,30 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     if (const char *env = getenv("NAPAFFT_DEBUG")) pp.debug = atoi(env);
     if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
     const unsigned grid = (unsigned)(pp.gsize * pp.ngroups);
+#ifndef NAPA_EMULATE
+    if (napa::pipe_staged(la, lb)) {
+        // tensor map of the column pass's source (pass A, or pass B of the inverse bit-reversed plan):
+        // doubles [item][row][2 * col], one box = one tile = L rows x C columns
+        const PassParams &cp = pk == 2 ? pp.b : pp.a;
+        const int lc = pk == 2 ? lb : la;
+        static tmap_encode_fn enc = nullptr;
+        if (!enc) {
+            void *fp = nullptr; cudaDriverEntryPointQueryResult qr;
+            CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr));
+            if (!fp || qr != cudaDriverEntryPointSuccess) return fail(NAPA_E_CUDA, "cuTensorMapEncodeTiled is not available");
+            enc = (tmap_encode_fn)fp;
+        }
+        const cuuint64_t B = (cuuint64_t)cp.s_i, L = 1ull << lc, C = 1ull << napa::plan_log2c(lc);
+        const cuuint64_t gdim[3] = { 2 * B, L, (cuuint64_t)pp.items };
+        const cuuint64_t gstr[2] = { B * sizeof(cplx), (cuuint64_t)cp.src_batch_stride * sizeof(cplx) };
+        const cuuint32_t box[3] = { (cuuint32_t)(2 * C), (cuuint32_t)L, 1 };
+        const cuuint32_t estr[3] = { 1, 1, 1 };
+        CUresult cr = enc((CUtensorMap *)pp.col_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)cp.src, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(NAPA_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    }
+#endif
 #ifdef NAPA_EMULATE
     NAPA_LAUNCH(fn, grid, napa::plan_threads(la), smem, st, pp);
 #else

@@ -202,10 +202,15 @@ template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, 
 __device__ __forceinline__ void st_data(cplx *p, cplx v, int, const L2Policies &) { *p = v; }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
 __device__ __forceinline__ void napa_nanosleep(unsigned) {}
-__device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int, const L2Policies &) { *s = *g; }
-__device__ __forceinline__ void cp_async_commit() {}
-__device__ __forceinline__ void cp_async_wait_all() {}
-__device__ __forceinline__ void l2_prefetch(const void *) {}
+// bulk-copy staging: the emulator copies synchronously and never waits
+__device__ __forceinline__ void mbar_init(unsigned long long *, unsigned) {}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *, unsigned) {}
+__device__ __forceinline__ void mbar_wait(unsigned long long *, unsigned) { __syncthreads(); }   // every thread waits once per staged tile
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void napa_syncwarp() {}
+__device__ __forceinline__ void bulk_g2s(cplx *s, const cplx *g, unsigned bytes, unsigned long long *, int, const L2Policies &) {
+    for (unsigned i = 0; i < bytes / sizeof(cplx); i++) s[i] = g[i];
+}
 #else
 struct L2Policies { unsigned long long normal, first, last; };
 __device__ __forceinline__ L2Policies make_policies() {
@@ -240,27 +245,42 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ void napa_nanosleep(unsigned ns) { __nanosleep(ns); }
-// 16-byte asynchronous global->shared copy, L2-only (.cg) hence coherent with other SMs' writes
-__device__ __forceinline__ void cp_async16(cplx *s, const cplx *g, int hint, const L2Policies &pol) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
-    const unsigned long long policy = pick_policy(pol, hint);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(sa), "l"(g), "l"(policy) : "memory");
+// mbarrier + bulk asynchronous copy (TMA engine, no tensor map): global -> shared, completion
+// counted in bytes on an mbarrier.  The copy goes through L2 only, hence sees other SMs' writes.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void l2_prefetch(const void *g) { asm volatile("prefetch.global.L2 [%0];" :: "l"(g)); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "NAPA_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra NAPA_MBAR_DONE;\n\t"
+        "bra NAPA_MBAR_WAIT;\n\t"
+        "NAPA_MBAR_DONE:\n\t"
+        "}" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// orders earlier generic-proxy accesses (made visible to this thread) before its later async-proxy operations
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void napa_syncwarp() { __syncwarp(); }
+// one whole column tile (L rows of C points, a 3-d box of the tensor map) in a single instruction
+__device__ __forceinline__ void tma_tile_g2s(cplx *s, const void *tmap, int x, int y, int z, unsigned long long *bar, int hint, const L2Policies &pol) {
+    const unsigned long long policy = pick_policy(pol, hint);
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 :: "r"((unsigned)__cvta_generic_to_shared(s)), "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                    "r"(x), "r"(y), "r"(z), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(cplx *s, const cplx *g, unsigned bytes, unsigned long long *bar, int hint, const L2Policies &pol) {
+    const unsigned long long policy = pick_policy(pol, hint);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"((unsigned)__cvta_generic_to_shared(s)), "l"(g), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)), "l"(policy) : "memory");
+}
 #endif
-// CTA-wide barrier, or a named barrier over the NT compute threads of a kernel that also runs a
-// control warp (persistent pipeline)
 struct SyncAll { static __device__ __forceinline__ void sync() { __syncthreads(); } };
-#ifdef NAPA_EMULATE
-__device__ __forceinline__ void named_bar_sync(int id, int count) { napa_emul::bar_sync(id, (unsigned)count); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { napa_emul::bar_arrive(id, (unsigned)count); }
-#else
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-#endif
-template <int NT> struct SyncCompute { static __device__ __forceinline__ void sync() { named_bar_sync(1, NT); } };
 
 // rev_w(x): reverse the low w bits of x (w = 0 -> 0)
 __device__ __forceinline__ int rev_bits(int x, int w) { return w ? (int)(__brev((unsigned)x) >> (32 - w)) : 0; }
@@ -484,10 +504,15 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 // used ones do not serialise the loads.
 // ALLOWED: the flag bits this instantiation can ever see (the persistent pipeline knows the role of
 // each pass at compile time; masking lets the compiler drop the other fusion paths = smaller code).
-template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook, unsigned ALLOWED = 0xffffffffu, bool HINTED = true>
+// STAGED: the tile's input was bulk-copied into `sm` itself (stage_issue below; rows of C points
+// for a column tile, C rows of L points for a row tile) and its arrival is awaited on `mbar`;
+// the exchange then reuses the same buffer (REUSE must be set).
+template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook, unsigned ALLOWED = 0xffffffffu, bool HINTED = true,
+          bool STAGED = false>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
                                          const long long src_item_delta, const long long dst_item_delta,
-                                         const L2Policies &pol, Hook &hook) {
+                                         const L2Policies &pol, Hook &hook,
+                                         unsigned long long *mbar = nullptr, const unsigned mbar_parity = 0) {
     constexpr int L = 1 << LOG2L;
     constexpr int T = L / 16;
     constexpr bool PLANAR = !(LM == MAP_Q && SM_ == MAP_Q);
@@ -519,7 +544,13 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
                 wv[m] = __ldg(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
             }
         }
-        if ((flags & PF_IN_REV) && !in_reorder) {
+        if constexpr (STAGED) {
+            static_assert(REUSE, "the staging buffer doubles as the exchange buffer");
+            constexpr int LC = plan_log2c(LOG2L);
+            mbar_wait(mbar, mbar_parity);
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = LM == MAP_Q ? sm[(lpos(m) << LC) + q] : sm[(q << LOG2L) + lpos(m)];
+        } else if ((flags & PF_IN_REV) && !in_reorder) {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i, src_hint, pol);
         } else {
@@ -624,22 +655,6 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     }
 }
 
-// Software L2 prefetch of a whole tile (one prefetch.global.L2 per 128-byte line).  Measured
-// neutral on B200 for this kernel (the limit was the LSU data pipe, not DRAM-side MLP); kept
-// for the debug knob only.
-template <int LOG2L, int LM>
-__device__ __forceinline__ void tile_l2_prefetch(const PassParams &p, const long long tile) {
-    constexpr int T = (1 << LOG2L) / 16;
-    const TileCtx c = tile_ctx<LOG2L, LM>(p, tile, p.flags);
-    if (!c.valid) return;
-    const cplx *src = p.src + c.item * p.src_batch_stride + c.s_xoff;
-#pragma unroll
-    for (int m = 0; m < 16; m++) {
-        const cplx *a = src + (long long)(c.t + m * T) * p.s_i;
-        if ((reinterpret_cast<unsigned long long>(a) & 127ull) == 0) l2_prefetch(a);
-    }
-}
-
 // Lane maps by tile kind: 0 = column-like (Q,Q); 1 = row-like (T,T); 2 = row-like load,
 // column-like (transposed) store (T,Q).  L < 128 always uses (Q,Q).
 __host__ __device__ constexpr int kind_lm(int l, int kind) { return l >= 7 && kind != 0 ? MAP_T : MAP_Q; }
@@ -675,7 +690,13 @@ fft_pass_kernel(const PassParams p) {
 //   PK 1: forward, bit-reversed output.  A = column digit src -> dst, B = row digit in place.
 //   PK 2: inverse of a bit-reversed input. A = row digit src -> dst, B = column digit in place.
 // ------------------------------------------------------------------------------------------
+#ifdef NAPA_EMULATE
+#define NAPA_GRID_CONSTANT
+#else
+#define NAPA_GRID_CONSTANT __grid_constant__
+#endif
 struct PipeParams {
+    alignas(64) unsigned long long col_tmap[16];   // CUtensorMap of the column pass's source: [item][row i][2*col] doubles, box = one tile
     PassParams a, b;                 // pass A (first executed) and pass B
     long long items;                 // batch
     int gsize, ngroups;              // CTAs per group, groups (grid = gsize * ngroups)
@@ -713,39 +734,141 @@ __device__ __forceinline__ void group_barrier(unsigned *ctr, const unsigned targ
     __syncthreads();
 }
 
+// Warp 0 starts the asynchronous copy of one tile's input into a staging buffer: L rows of C
+// contiguous points (column tile, lane map Q) or C rows of L contiguous points (row tile, map T).
+template <int LOG2L, int LM>
+__device__ __forceinline__ void stage_issue(const PassParams &p, const long long tile, const long long src_item_delta,
+                                            cplx *buf, unsigned long long *mbar, const L2Policies &pol, const void *col_tmap) {
+    constexpr int L = 1 << LOG2L, LC = plan_log2c(LOG2L), C = 1 << LC;
+    const int lane = (int)threadIdx.x & 31;
+    const long long b = tile >> p.lg_tpi;
+    const int r = (int)(tile & (p.tiles_per_item - 1));
+    const int ra = r >> p.lg_G, rg = r & (p.G - 1);
+    const cplx *base = p.src + (b + src_item_delta) * p.src_batch_stride + (long long)ra * p.s_SA + (long long)rg * p.s_SG;
+    fence_proxy_async();           // the buffer's last generic-proxy accesses and (pass B) the other CTAs' stores come first
+    if (lane == 0) mbar_expect_tx(mbar, (unsigned)(L * C * sizeof(cplx)));
+    napa_syncwarp();
+    if (LM == MAP_Q) {
+#ifdef NAPA_EMULATE
+        (void)col_tmap;
+        for (int i = lane; i < L; i += 32) bulk_g2s(buf + (i << LC), base + (long long)i * p.s_i, (unsigned)(C * sizeof(cplx)), mbar, p.src_hint, pol);
+#else
+        // column pass of a two-digit plan: a = 0, the tile is columns [rg*C, rg*C + C) of item b
+        if (lane == 0) tma_tile_g2s(buf, col_tmap, 2 * rg * C, 0, (int)(b + src_item_delta), mbar, p.src_hint, pol);
+#endif
+    } else {
+        for (int q = lane; q < C; q += 32) bulk_g2s(buf + (q << LOG2L), base + (long long)q * p.s_q, (unsigned)(L * sizeof(cplx)), mbar, p.src_hint, pol);
+    }
+}
+
+// Tiles of 2048 points (both digits <= 2^8) are fed by bulk copies, double-buffered: while a CTA
+// computes tile k out of one buffer, the input of its tile k+1 lands in the other, so the global
+// load latency is off the critical path and three CTAs per SM keep the issue slots busy.
+__host__ __device__ constexpr bool pipe_staged(int la, int lb) { return la <= NAPA_SMALL_TILE_MAXL && lb <= NAPA_SMALL_TILE_MAXL; }
+__host__ __device__ constexpr bool pipe_stage_a(int pk) { return pk != 2; }   // PK 2 pass A: bit-reversed rows go through the reorder buffer
+__host__ __device__ constexpr size_t pipe_buf_bytes(int la, int lb, int pk) {
+    const size_t a = kind_smem_bytes(la, pipe_kind_a(pk)), b = kind_smem_bytes(lb, pipe_kind_b(pk));
+    return ((a > b ? a : b) + 127) / 128 * 128;
+}
+__host__ __device__ constexpr size_t pipe_smem_bytes(int la, int lb, int pk) {
+    return pipe_staged(la, lb) ? 2 * pipe_buf_bytes(la, lb, pk) + 16 : pipe_buf_bytes(la, lb, pk);
+}
+__host__ __device__ constexpr int pipe_min_ctas(int la, int lb) { return pipe_staged(la, lb) ? 3 : plan_min_ctas(la); }
+
 template <int LA, int LB, int PK>
-__global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_pipeline_kernel(const PipeParams p) {
+__global__ void __launch_bounds__(plan_threads(LA), pipe_min_ctas(LA, LB)) fft_pipeline_kernel(const NAPA_GRID_CONSTANT PipeParams p) {
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a fused pair use the same tile shape");
     constexpr int KA = pipe_kind_a(PK), KB = pipe_kind_b(PK);
+    constexpr bool ST = pipe_staged(LA, LB), STA = ST && pipe_stage_a(PK), STB = ST;
     NAPA_DYN_SMEM(cplx, sm);
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     NoHook nh;
     const int g = (int)blockIdx.x / p.gsize, r = (int)blockIdx.x - g * p.gsize;
     unsigned *ctr = p.bar + 32 * g;
     unsigned arrivals = 0;
-    for (long long item = g; item < p.items; item += p.ngroups) {
-        const long long delta = (long long)g - item;
-        bool first = true;
-        for (int t = r; t < p.tiles_a; t += p.gsize) {
-            if (!first) __syncthreads();       // previous tile is done with sm
-            first = false;
-            run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, pipe_flags_a(PK)>(
-                p.a, item * p.tiles_a + t, sm, 0, p.a_dst_is_ring ? delta : 0, pol, nh);
-        }
-        arrivals += (unsigned)p.gsize;
-        group_barrier(ctr, arrivals, p.error);
-        first = true;
-        for (int t = r; t < p.tiles_b; t += p.gsize) {
-            if (!first) __syncthreads();
-            first = false;
-            run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, NoHook, pipe_flags_b(PK)>(
-                p.b, item * p.tiles_b + t, sm, p.b_src_is_ring ? delta : 0, 0, pol, nh);
-        }
-        if (PK == 0) {                          // the slot is rewritten by the next transform's pass A
+    if constexpr (!ST) {
+        for (long long item = g; item < p.items; item += p.ngroups) {
+            const long long delta = (long long)g - item;
+            bool first = true;
+            for (int t = r; t < p.tiles_a; t += p.gsize) {
+                if (!first) __syncthreads();       // previous tile is done with sm
+                first = false;
+                run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, pipe_flags_a(PK)>(
+                    p.a, item * p.tiles_a + t, sm, 0, p.a_dst_is_ring ? delta : 0, pol, nh);
+            }
             arrivals += (unsigned)p.gsize;
             group_barrier(ctr, arrivals, p.error);
-        } else {
-            __syncthreads();
+            first = true;
+            for (int t = r; t < p.tiles_b; t += p.gsize) {
+                if (!first) __syncthreads();
+                first = false;
+                run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, NoHook, pipe_flags_b(PK)>(
+                    p.b, item * p.tiles_b + t, sm, p.b_src_is_ring ? delta : 0, 0, pol, nh);
+            }
+            if (PK == 0) {                          // the slot is rewritten by the next transform's pass A
+                arrivals += (unsigned)p.gsize;
+                group_barrier(ctr, arrivals, p.error);
+            } else {
+                __syncthreads();
+            }
+        }
+    } else {
+        constexpr size_t BUF = pipe_buf_bytes(LA, LB, PK) / sizeof(cplx);
+        unsigned long long *mbar = reinterpret_cast<unsigned long long *>(sm + 2 * BUF);
+        if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); fence_proxy_async(); }
+        __syncthreads();
+        const int nA = (p.tiles_a - r + p.gsize - 1) / p.gsize, nB = (p.tiles_b - r + p.gsize - 1) / p.gsize;
+        const bool warp0 = threadIdx.x < 32;
+        unsigned parity = 0;                   // bit b: phase parity of mbar[b]
+        int k = 0;                             // tiles done by this CTA: tile k lives in buf[k & 1]
+        bool have = false;                     // the current tile's input is already on its way
+        for (long long item = g; item < p.items; item += p.ngroups) {
+            const long long delta = (long long)g - item;
+            for (int s = 0; s < nA + nB; s++, k++) {
+                const bool is_a = s < nA;
+                // barriers: before the first B tile (the group's A output is complete), and for the
+                // scratch slot of PK 0 before the next transform's A tiles store into it
+                if (s == nA || (PK == 0 && s == 0 && item != (long long)g)) {
+                    arrivals += (unsigned)p.gsize;
+                    group_barrier(ctr, arrivals, p.error);
+                } else {
+                    __syncthreads();               // previous tile is done with both buffers' generic accesses
+                }
+                const int cb = k & 1, nb = cb ^ 1;
+                // the tile after this one
+                int s2 = s + 1; long long item2 = item;
+                if (s2 == nA + nB) { s2 = 0; item2 += p.ngroups; }
+                const bool next_exists = item2 < p.items;
+                const bool next_a = s2 < nA;
+                // not across the A -> B barrier (the data is not there yet), and only staged passes
+                const bool prefetch = next_exists && s2 != nA && (next_a ? STA : STB);
+                if (warp0) {
+                    if (!have) {
+                        if (is_a) { if constexpr (STA) stage_issue<LA, kind_lm(LA, KA)>(p.a, item * p.tiles_a + r + s * p.gsize, 0, (sm + cb * BUF), mbar + cb, pol, p.col_tmap); }
+                        else stage_issue<LB, kind_lm(LB, KB)>(p.b, item * p.tiles_b + r + (s - nA) * p.gsize, p.b_src_is_ring ? delta : 0, (sm + cb * BUF), mbar + cb, pol, p.col_tmap);
+                    }
+                    if (prefetch) {
+                        const long long delta2 = (long long)g - item2;
+                        if (next_a) { if constexpr (STA) stage_issue<LA, kind_lm(LA, KA)>(p.a, item2 * p.tiles_a + r + s2 * p.gsize, 0, (sm + nb * BUF), mbar + nb, pol, p.col_tmap); }
+                        else stage_issue<LB, kind_lm(LB, KB)>(p.b, item2 * p.tiles_b + r + (s2 - nA) * p.gsize, p.b_src_is_ring ? delta2 : 0, (sm + nb * BUF), mbar + nb, pol, p.col_tmap);
+                    }
+                }
+                if (is_a) {
+                    if constexpr (STA) {
+                        run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, true, NoHook, pipe_flags_a(PK), true, true>(
+                            p.a, item * p.tiles_a + r + s * p.gsize, (sm + cb * BUF), 0, p.a_dst_is_ring ? delta : 0, pol, nh, mbar + cb, (parity >> cb) & 1u);
+                        parity ^= 1u << cb;
+                    } else {
+                        run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, pipe_flags_a(PK)>(
+                            p.a, item * p.tiles_a + r + s * p.gsize, (sm + cb * BUF), 0, p.a_dst_is_ring ? delta : 0, pol, nh);
+                    }
+                } else {
+                    run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, true, NoHook, pipe_flags_b(PK), true, true>(
+                        p.b, item * p.tiles_b + r + (s - nA) * p.gsize, (sm + cb * BUF), p.b_src_is_ring ? delta : 0, 0, pol, nh, mbar + cb, (parity >> cb) & 1u);
+                    parity ^= 1u << cb;
+                }
+                have = prefetch;
+            }
         }
     }
 }
