@@ -115,6 +115,7 @@ def run_reference_arm(args):
     n, batch, desc = WORKLOADS[wl]
     threads = os.cpu_count() or 1
     items = min(batch, (64 if n <= (1 << 16) else 4) * threads)      # ~1 s of host work per step
+    threads = max(1, min(threads, items))
     state = cpu_oracle_state(wl, items)
     for _ in range(args.warmup):
         cpu_oracle_step(wl, items, threads, state)
@@ -197,6 +198,9 @@ class ClockSampler:
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def main():
+    # keep stdout to the one JSON line: NCCL's version banner goes to stdout at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -356,8 +360,8 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        items = min(batch, 2 * threads)
+        items = min(batch, 2 * (os.cpu_count() or 1))
+        threads = max(1, min(os.cpu_count() or 1, items))       # threads actually used (1 for the single-transform config)
         st = cpu_oracle_state(wl, items)
         cpu_oracle_step(wl, items, threads, st)
         t0 = time.perf_counter(); reps = 0
