@@ -53,6 +53,11 @@ typedef enum {
 #define NAPA_WINDOW_NONE 0
 #define NAPA_WINDOW_REAL 1    /* float, real-sample       */
 #define NAPA_WINDOW_COMPLEX 2 /* complex, complex-sample  */
+/* input sample types accepted by complex-samplify (support.lisp:64-93) on the device */
+#define NAPA_SAMPLE_C64 0 /* (complex double-float): no conversion */
+#define NAPA_SAMPLE_F64 1 /* double-float reals          */
+#define NAPA_SAMPLE_C32 2 /* (complex single-float)      */
+#define NAPA_SAMPLE_F32 3 /* single-float reals          */
 /* element type of bit-reverse: interface.lisp:103-104 */
 #define NAPA_ELT_COMPLEX 0
 #define NAPA_ELT_REAL 1
@@ -84,6 +89,13 @@ uint64_t napafft_launch_count(void);
 int napafft_c2c(const double *src, double *dst, size_t n, size_t batch, size_t stride, int dir, int scale,
                 int in_order, const void *window, int window_type, int window_per_batch);
 
+/* napafft_c2c for an input that the reference would first pass through complex-samplify
+ * (support.lisp:64-93; fft / ifft call it on every argument, easy-interface.lisp:50, 75): src holds
+ * batch x n samples of src_type, dense; the raw samples are what crosses PCIe and the widening to
+ * complex double happens on the device.  dst: batch x n complex, must not alias src. */
+int napafft_c2c_typed(const void *src, int src_type, double *dst, size_t n, size_t batch, int dir, int scale,
+                      int in_order, const void *window, int window_type, int window_per_batch);
+
 /* Replaces %ensure-reverse / get-reverse / bit-reverse (interface.lisp:103-133,
  * easy-interface.lisp:10-37): dst[b*stride + i] = src[b*stride + rev(i)], i < n. */
 int napafft_bit_reverse(const void *src, void *dst, size_t n, size_t batch, size_t stride, int elt);
@@ -98,6 +110,15 @@ int napafft_rifft(const double *src, double *dst, size_t n, size_t batch, int sc
 /* Replaces %2rfft (real.lisp:33-48): dst = batch x 2n complex, [0,n) = FFT(v1), [n,2n) = FFT(v2) */
 int napafft_2rfft(const double *v1, const double *v2, double *dst, size_t n, size_t batch, int scale);
 
+/* The overlap-add streaming filter of example.lisp:81-114 / README:708-741 (filter-chunks) as one
+ * device pipeline: half-overlapping chunks of `chunk` samples (zero-padded past
+ * len), each windowed-fft'ed (:in-order nil) with `window` (chunk doubles; the reference uses
+ * (window-vector 'triangle chunk)), multiplied by `filter_rev` (chunk doubles: the filter in
+ * bit-reversed order, (bit-reverse filter)) inside ifft :in-order nil, renormalised to
+ * 0.5 * sqrt(energy-in / energy-out) and accumulated.  vector: len doubles; dst: len complex. */
+int napafft_filter_chunks(const double *vector, size_t len, const double *filter_rev, const double *window, size_t chunk,
+                          double *dst);
+
 /* Page-lock / unlock a caller-owned host range so that the entry points above DMA straight from
  * and to it (SBCL: a static vector or a pinned foreign block).  Optional. */
 int napafft_host_register(void *ptr, size_t bytes);
@@ -111,6 +132,10 @@ int napafft_bit_reverse_dev(const void *src, void *dst, size_t n, size_t batch, 
 int napafft_rfft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream);
 int napafft_rifft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream);
 int napafft_2rfft_dev(const void *v1, const void *v2, void *dst, size_t n, size_t batch, int scale, void *stream);
+int napafft_filter_chunks_dev(const void *vector, size_t len, const void *filter_rev, const void *window, size_t chunk,
+                              void *dst, void *stream);
+/* complex-samplify alone: dst[i] = (complex double) src[i], i < count */
+int napafft_widen_dev(const void *src, int src_type, void *dst, size_t count, void *stream);
 /* a[b*n + i] *= h[b*h_stride + i]  (pointwise spectrum product; h_stride 0 = shared filter) */
 int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, size_t h_stride, void *stream);
 

@@ -28,6 +28,7 @@ rifft = _default.rifft
 two_rfft = _default.two_rfft                # %2rfft
 windowed_rfft = _default.windowed_rfft
 windowed_rifft = _default.windowed_rifft
+filter_chunks = _default.filter_chunks      # example.lisp:81-114
 get_fft = _default.get_fft
 get_windowed_fft = _default.get_windowed_fft
 get_reverse = _default.get_reverse

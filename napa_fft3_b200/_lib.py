@@ -18,12 +18,13 @@ FWD, INV = 1, -1
 SCALE_NONE, SCALE_INV, SCALE_SQRT = 0, 1, 2
 WINDOW_NONE, WINDOW_REAL, WINDOW_COMPLEX = 0, 1, 2
 ELT_COMPLEX, ELT_REAL = 0, 1
+SAMPLE_C64, SAMPLE_F64, SAMPLE_C32, SAMPLE_F32 = 0, 1, 2, 3
 
 # every symbol include/napafft.h declares (tests check that the .so exports all of them)
 ABI_SYMBOLS = [
     "napafft_init", "napafft_shutdown", "napafft_abi_version", "napafft_last_error", "napafft_launch_count",
     "napafft_c2c", "napafft_bit_reverse", "napafft_rfft", "napafft_rifft", "napafft_2rfft",
-    "napafft_host_register", "napafft_host_unregister",
+    "napafft_filter_chunks", "napafft_filter_chunks_dev", "napafft_c2c_typed", "napafft_widen_dev", "napafft_host_register", "napafft_host_unregister",
     "napafft_c2c_dev", "napafft_bit_reverse_dev", "napafft_rfft_dev", "napafft_rifft_dev", "napafft_2rfft_dev",
     "napafft_cmul_dev", "napafft_c2c_cols_dev", "napafft_relayout_dev", "napafft_dev_alloc", "napafft_dev_free", "napafft_dev_upload", "napafft_dev_download",
     "napafft_dev_sync", "napafft_scale_factor", "napafft_radix2_twiddle",
@@ -57,6 +58,10 @@ class Binding:
         L.napafft_rfft.argtypes = [vp, vp, sz, sz, i]
         L.napafft_rifft.argtypes = [vp, vp, sz, sz, i]
         L.napafft_2rfft.argtypes = [vp, vp, vp, sz, sz, i]
+        L.napafft_c2c_typed.argtypes = [vp, i, vp, sz, sz, i, i, i, vp, i, i]
+        L.napafft_widen_dev.argtypes = [vp, i, vp, sz, vp]
+        L.napafft_filter_chunks.argtypes = [vp, sz, vp, vp, sz, vp]
+        L.napafft_filter_chunks_dev.argtypes = [vp, sz, vp, vp, sz, vp, vp]
         L.napafft_host_register.argtypes = [vp, sz]
         L.napafft_host_unregister.argtypes = [vp]
         L.napafft_c2c_dev.argtypes = [vp, vp, sz, sz, sz, i, i, i, vp, i, i, vp]

@@ -77,6 +77,7 @@ struct State {
     void *dbuf[2] = {}; size_t dbuf_bytes = 0;
     void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = (size_t)1 << 30; // items per launch of the multi-launch path (also the natural-order scratch size)
+    void *oa_buf = nullptr; size_t oa_bytes = 0;   // chunk matrix + energies of the overlap-add filter
     size_t pipe_l2_bytes = 40u << 20;     // live intermediate of the group-fused kernel (groups * n * 16 B)
     int pipe_gsize = 0;                   // CTAs per group (0 = auto)
     bool use_pipeline = false;            // persistent L2 pipeline: measured slower than two plain launches
@@ -845,6 +846,42 @@ static int exec_2rfft(const double *v1, const double *v2, cplx *dst, size_t n, s
 }
 
 // ------------------------------------------------------------------------------------------
+// example.lisp:81-114 (filter-chunks) on the device.  vector: len reals; window: chunk reals (the
+// triangle window of the reference's windowed-fft call); filter_rev: chunk reals, the filter in
+// bit-reversed order; dst: len complex.
+// ------------------------------------------------------------------------------------------
+static int exec_filter_chunks(const double *vec, size_t len, const double *filter_rev, const double *window, size_t chunk,
+                              cplx *dst, cudaStream_t st) {
+    if (len == 0) return NAPA_OK;
+    const int lgc = ilog2(chunk);
+    const size_t half = chunk / 2, nchunks = (len + half - 1) / half;
+    const size_t need = nchunks * chunk * sizeof(cplx) + 2 * nchunks * sizeof(double) + 256;
+    if (G.oa_bytes < need) {
+        CU(cudaDeviceSynchronize());
+        if (G.oa_buf) CU(cudaFree(G.oa_buf));
+        G.oa_buf = nullptr; G.oa_bytes = 0;
+        CU(cudaMalloc(&G.oa_buf, need));
+        G.oa_bytes = need;
+    }
+    cplx *X = (cplx *)G.oa_buf;
+    double *e_old = (double *)(X + nchunks * chunk), *e_new = e_old + nchunks;
+    NAPA_LAUNCH(napa::oa_gather_kernel, (unsigned)nchunks, 256, 0, st, vec, (long long)len, X, e_old, lgc);
+    g_launches++;
+    C2COpts f{};
+    f.dir = NAPA_FWD; f.in_order = 0; f.scale = 1.0; f.window = window; f.wtype = NAPA_WINDOW_REAL;
+    OK(exec_c2c(X, X, chunk, nchunks, chunk, chunk, f, st));
+    C2COpts b{};
+    b.dir = NAPA_INV; b.in_order = 0; b.scale = scale_factor(chunk, NAPA_INV, NAPA_SCALE_INV); b.window = filter_rev; b.wtype = NAPA_WINDOW_REAL;
+    OK(exec_c2c(X, X, chunk, nchunks, chunk, chunk, b, st));
+    NAPA_LAUNCH(napa::oa_energy_kernel, (unsigned)nchunks, 256, 0, st, (const cplx *)X, e_new, lgc);
+    NAPA_LAUNCH(napa::oa_add_kernel, (unsigned)((len + 255) / 256), 256, 0, st, (const cplx *)X, (const double *)e_old,
+                (const double *)e_new, dst, (long long)len, lgc);
+    g_launches += 2;
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // argument checks shared by host and device entry points
 // ------------------------------------------------------------------------------------------
 static int check_c2c_args(const void *src, const void *dst, size_t n, size_t batch, size_t stride, int dir, int scale,
@@ -928,7 +965,7 @@ static int run_host_job(const HostJob &j, Body body) {
     size_t target = (size_t)256 << 20;                                    // device bytes per chunk
     if (const char *e = getenv("NAPAFFT_STAGE_MB")) target = (size_t)atoll(e) << 20;
     const size_t items = std::max<size_t>(1, std::min(j.batch, target / std::max<size_t>(per_item, 1)));
-    OK(ensure_staging(items * per_item));
+    OK(ensure_staging(items * per_item + 256));
     const bool src_pinned = is_pinned(j.src) && (!j.src2 || is_pinned(j.src2));
     const bool dst_pinned = is_pinned(j.dst);
     if (!src_pinned || !dst_pinned) OK(ensure_pinned(items * std::max(in_total, j.out_item_bytes)));
@@ -950,7 +987,7 @@ static int run_host_job(const HostJob &j, Body body) {
         OK(drain(slot));
         cudaStream_t st = G.stream[slot];
         char *dev_in = (char *)G.dbuf[slot];
-        char *dev_out = j.inplace ? dev_in : dev_in + nb * in_total;
+        char *dev_out = j.inplace ? dev_in : dev_in + ((nb * in_total + 255) & ~(size_t)255);    // keep the output 256-byte aligned
         for (int which = 0; which < (j.src2 ? 2 : 1); which++) {
             const char *hs = which ? j.src2 : j.src;
             char *dd = dev_in + (which ? nb * j.in_item_bytes : 0);
@@ -1023,6 +1060,7 @@ NAPA_API int napafft_shutdown(void) {
     for (auto &kv : G.pairs) cudaFree(kv.second.dev);
     G.pairs.clear();
     if (G.scratch) cudaFree(G.scratch);
+    if (G.oa_buf) { cudaFree(G.oa_buf); G.oa_buf = nullptr; G.oa_bytes = 0; }
     G.scratch = nullptr; G.scratch_bytes = 0;
     for (auto &kv : G.counters) cudaFree(kv.second.first);
     G.counters.clear();
@@ -1113,6 +1151,44 @@ NAPA_API int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, si
     return NAPA_OK;
 }
 
+static int check_filter_args(const void *vec, const void *filter_rev, const void *window, size_t chunk, const void *dst) {
+    if (!vec || !filter_rev || !window || !dst) return fail(NAPA_E_NULL, "vector / filter / window / dst must not be NULL");
+    if (!pow2(chunk) || chunk < 2) return fail(NAPA_E_NOT_POW2, "chunk size %zu is not a power of two >= 2", chunk);
+    if (chunk > ((size_t)1 << 32)) return fail(NAPA_E_UNSUPPORTED, "chunk size %zu exceeds 2^32", chunk);
+    return NAPA_OK;
+}
+NAPA_API int napafft_filter_chunks_dev(const void *vector, size_t len, const void *filter_rev, const void *window, size_t chunk,
+                                       void *dst, void *stream) {
+    OK(check_filter_args(vector, filter_rev, window, chunk, dst));
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    return exec_filter_chunks((const double *)vector, len, (const double *)filter_rev, (const double *)window, chunk, (cplx *)dst,
+                              (cudaStream_t)stream);
+}
+NAPA_API int napafft_filter_chunks(const double *vector, size_t len, const double *filter_rev, const double *window, size_t chunk,
+                                   double *dst) {
+    OK(check_filter_args(vector, filter_rev, window, chunk, dst));
+    if (len == 0) return NAPA_OK;
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    OK(ensure_staging(0));
+    cudaStream_t st = G.stream[0];
+    double *d_vec = nullptr, *d_f = nullptr, *d_w = nullptr; cplx *d_dst = nullptr;
+    int rc = NAPA_OK;
+    auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == NAPA_OK) rc = fail(NAPA_E_CUDA, "%s", cudaGetErrorString(e)); return e == cudaSuccess; };
+    if (cu(cudaMalloc(&d_vec, len * 8)) && cu(cudaMalloc(&d_f, chunk * 8)) && cu(cudaMalloc(&d_w, chunk * 8)) &&
+        cu(cudaMalloc(&d_dst, len * sizeof(cplx)))) {
+        cu(cudaMemcpyAsync(d_vec, vector, len * 8, cudaMemcpyHostToDevice, st));
+        cu(cudaMemcpyAsync(d_f, filter_rev, chunk * 8, cudaMemcpyHostToDevice, st));
+        cu(cudaMemcpyAsync(d_w, window, chunk * 8, cudaMemcpyHostToDevice, st));
+        if (rc == NAPA_OK) rc = exec_filter_chunks(d_vec, len, d_f, d_w, chunk, d_dst, st);
+        if (rc == NAPA_OK) cu(cudaMemcpyAsync(dst, d_dst, len * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+        cu(cudaStreamSynchronize(st));
+    }
+    cudaFree(d_vec); cudaFree(d_f); cudaFree(d_w); cudaFree(d_dst);
+    return rc;
+}
+
 NAPA_API int napafft_c2c_cols_dev(const void *src, void *dst, size_t n1, size_t cols, int dir, double scale,
                                   int lg_twiddle_modulus, long long col_offset, void *stream) {
     if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
@@ -1192,6 +1268,52 @@ NAPA_API int napafft_c2c(const double *src, double *dst, size_t n, size_t batch,
         o.wtype = window_type; o.wpb = window_per_batch;
         o.window = window_per_batch && dwin ? (const char *)dwin + b0 * n * (window_type == NAPA_WINDOW_REAL ? 8 : 16) : dwin;
         return exec_c2c((const cplx *)din, (cplx *)dout, n, nb, n, n, o, st);
+    });
+}
+
+static size_t sample_bytes(int src_type) { return src_type == NAPA_SAMPLE_C64 ? 16 : (src_type == NAPA_SAMPLE_F32 ? 4 : 8); }
+static int exec_widen(const void *src, int src_type, cplx *dst, size_t total, cudaStream_t st) {
+    if (total == 0) return NAPA_OK;
+    if (src_type == NAPA_SAMPLE_C64) { CU(cudaMemcpyAsync(dst, src, total * sizeof(cplx), cudaMemcpyDeviceToDevice, st)); return NAPA_OK; }
+    NAPA_LAUNCH(napa::widen_kernel, (unsigned)((total + 255) / 256), 256, 0, st, src, src_type, dst, (long long)total);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NAPA_OK;
+}
+NAPA_API int napafft_widen_dev(const void *src, int src_type, void *dst, size_t count, void *stream) {
+    if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (src_type < 0 || src_type > 3) return fail(NAPA_E_BAD_ENUM, "sample type %d is not 0 .. 3", src_type);
+    OK(ensure_init());
+    return exec_widen(src, src_type, (cplx *)dst, count, (cudaStream_t)stream);
+}
+// napafft_c2c on an input that still needs complex-samplify: the raw samples cross PCIe, the
+// widening happens on the device.  Items are dense (n samples apart) on both sides.
+NAPA_API int napafft_c2c_typed(const void *src, int src_type, double *dst, size_t n, size_t batch, int dir, int scale,
+                               int in_order, const void *window, int window_type, int window_per_batch) {
+    OK(check_c2c_args(src, dst, n, batch, n, dir, scale, window, window_type));
+    if (src_type < 0 || src_type > 3) return fail(NAPA_E_BAD_ENUM, "sample type %d is not 0 .. 3", src_type);
+    if (src_type == NAPA_SAMPLE_C64)
+        return napafft_c2c((const double *)src, dst, n, batch, n, dir, scale, in_order, window, window_type, window_per_batch);
+    if ((const void *)src == (const void *)dst) return fail(NAPA_E_UNSUPPORTED, "a typed input cannot alias the complex destination");
+    if (batch == 0) return NAPA_OK;
+    OK(ensure_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    OK(ensure_staging(16));
+    const void *dwin;
+    OK(upload_window(window, window_type, window_per_batch ? n * batch : n, &dwin));
+    const size_t es = sample_bytes(src_type);
+    HostJob j;
+    j.src = (const char *)src; j.in_item_bytes = n * es; j.in_pitch = n * es;
+    j.dst = (char *)dst; j.out_item_bytes = n * 16; j.out_pitch = n * 16;
+    j.inplace = false; j.batch = batch;
+    const double sf = scale_factor(n, dir, scale);
+    return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t b0, cudaStream_t st) -> int {
+        OK(exec_widen(din, src_type, (cplx *)dout, nb * n, st));
+        C2COpts o{};
+        o.dir = dir; o.in_order = in_order; o.scale = sf;
+        o.wtype = window_type; o.wpb = window_per_batch;
+        o.window = window_per_batch && dwin ? (const char *)dwin + b0 * n * (window_type == NAPA_WINDOW_REAL ? 8 : 16) : dwin;
+        return exec_c2c((const cplx *)dout, (cplx *)dout, n, nb, n, n, o, st);
     });
 }
 

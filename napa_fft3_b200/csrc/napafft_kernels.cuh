@@ -26,6 +26,7 @@
     T *name = reinterpret_cast<T *>(name##_raw)
 #define NAPA_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
+#include <math.h>
 #include <stdint.h>
 
 namespace napa {
@@ -978,6 +979,83 @@ __global__ void __launch_bounds__(256) bitrev_small_kernel(const E *src, E *dst,
         const int r = rev_bits(i, w);
         d[i] = sm[r];
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// complex-samplify on the device (support.lisp:64-93): real double / complex single / real single
+// input widened to complex double, so that the host ships 8 or 4 bytes per sample over PCIe
+// instead of 16.  src_type: 1 = f64 real, 2 = complex f32, 3 = f32 real.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) widen_kernel(const void *__restrict__ src, int src_type, cplx *dst, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    cplx v;
+    if (src_type == 1) v = make_double2(reinterpret_cast<const double *>(src)[i], 0.0);
+    else if (src_type == 2) { const float *f = reinterpret_cast<const float *>(src) + 2 * i; v = make_double2((double)f[0], (double)f[1]); }
+    else v = make_double2((double)reinterpret_cast<const float *>(src)[i], 0.0);
+    dst[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Overlap-add streaming filter (example.lisp:81-114, filter-chunks): half-overlapping chunks of a
+// real signal, each windowed-fft'ed, multiplied by a filter in the bit-reversed spectrum, inverse
+// transformed, renormalised to its input energy and accumulated.  The chunks are independent, so
+// the whole signal is one batch: gather (+ energy), two batched c2c launches, energy, overlap-add.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double x) {
+    __shared__ double red[256];
+    red[threadIdx.x] = x;
+    __syncthreads();
+#pragma unroll
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+// chunk c = samples [c*half, c*half + chunk) zero-padded past `len`, widened to complex; energy[c] = sum |x|^2
+__global__ void __launch_bounds__(256) oa_gather_kernel(const double *__restrict__ vec, long long len, cplx *X,
+                                                        double *energy, int lg_chunk) {
+    const long long chunk = 1LL << lg_chunk, half = chunk >> 1;
+    const long long base = (long long)blockIdx.x * half;
+    cplx *x = X + (long long)blockIdx.x * chunk;
+    double acc = 0.0;
+    for (long long j = threadIdx.x; j < chunk; j += 256) {
+        const double v = base + j < len ? vec[base + j] : 0.0;
+        x[j] = make_double2(v, 0.0);
+        acc += v * v;
+    }
+    acc = block_sum_256(acc);
+    if (threadIdx.x == 0) energy[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(256) oa_energy_kernel(const cplx *__restrict__ X, double *energy, int lg_chunk) {
+    const long long chunk = 1LL << lg_chunk;
+    const cplx *x = X + (long long)blockIdx.x * chunk;
+    double acc = 0.0;
+    for (long long j = threadIdx.x; j < chunk; j += 256) { const cplx v = x[j]; acc += v.x * v.x + v.y * v.y; }
+    acc = block_sum_256(acc);
+    if (threadIdx.x == 0) energy[blockIdx.x] = acc;
+}
+// dst[j] = (0 + s(c0) * X[c0][j - c0*half]) + s(c1) * X[c1][j - c1*half], c1 = j / half, c0 = c1 - 1:
+// the accumulation order of the reference's chunk loop; s(c) = 0.5 * sqrt(e_old[c] / e_new[c])
+__global__ void __launch_bounds__(256) oa_add_kernel(const cplx *__restrict__ X, const double *__restrict__ e_old,
+                                                     const double *__restrict__ e_new, cplx *dst, long long len, int lg_chunk) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    const long long chunk = 1LL << lg_chunk, half = chunk >> 1;
+    const long long c1 = j >> (lg_chunk - 1), c0 = c1 - 1;
+    cplx acc = make_double2(0.0, 0.0);
+    if (c0 >= 0) {
+        const double s0 = 0.5 * sqrt(e_old[c0] / e_new[c0]);
+        const cplx a = X[c0 * chunk + (j - c0 * half)];
+        acc = make_double2(s0 * a.x, s0 * a.y);
+    }
+    const double s1 = 0.5 * sqrt(e_old[c1] / e_new[c1]);
+    const cplx b = X[c1 * chunk + (j - c1 * half)];
+    acc.x += s1 * b.x; acc.y += s1 * b.y;
+    dst[j] = acc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -225,11 +225,32 @@ class NapaFFT:
             raise NapaFFTError(2, f"window of length {len(window)} shorter than the transform ({n})")
         return _ptr(window), wt, window
 
+    @staticmethod
+    def _typed_input(vec, n):
+        """(array, NAPA_SAMPLE_*) when `vec` is a dense numpy vector of exactly n real-double, complex-single or
+        real-single samples -- the inputs complex-samplify (support.lisp:64-93) would widen on the host."""
+        if not isinstance(vec, np.ndarray) or vec.ndim != 1 or len(vec) != n or not vec.flags.c_contiguous:
+            return None
+        code = {np.dtype(np.float64): _lib.SAMPLE_F64, np.dtype(np.complex64): _lib.SAMPLE_C32,
+                np.dtype(np.float32): _lib.SAMPLE_F32}.get(vec.dtype)
+        return None if code is None else (vec, code)
+
     def _c2c(self, vec, dst, size, in_order, scale, window, direction):
         n = size if size is not None else len(vec)
         if dst is not None and not _is_complex_sample_array(dst):
             raise TypeError("dst must be a complex-sample-array or NIL")
         old = vec
+        fast = self._typed_input(vec, n)
+        if fast is not None and power_of_two_p(n):
+            # complex-samplify on the device: the raw samples cross PCIe (8 or 4 bytes instead of 16)
+            raw, code = fast
+            if dst is None:
+                dst = np.empty(n, dtype=np.complex128)     # the coerced copy of the reference, transformed in place
+            elif len(dst) < n:
+                raise NapaFFTError(2, f"destination of length {len(dst)} shorter than size {n}")
+            wptr, wt, _keep = self._window_args(window, n)
+            self.b.c2c_typed(_ptr(raw), code, _ptr(dst), n, 1, direction, _scale_code(scale), int(bool(in_order)), wptr, wt, 0)
+            return dst
         vec = complex_samplify(vec, n)
         if not power_of_two_p(n):
             raise NapaFFTError(1, f"transform size {n} is not a power of two")
@@ -479,6 +500,23 @@ class NapaFFT:
         if len(dst) < 2 * n:
             raise NapaFFTError(2, f"destination of length {len(dst)} shorter than 2n = {2 * n}")
         self.b.__getattr__("2rfft")(_ptr(v1), _ptr(v2), _ptr(dst), n, 1, sc)
+        return dst
+
+    # ---- example.lisp ---------------------------------------------------------------------
+    def filter_chunks(self, vector, filter):
+        """example.lisp:81-114 (README:708-741): overlap-add streaming filter.  Half-overlapping chunks of
+        len(filter) samples, each `windowed-fft ... :window-fn 'triangle :in-order nil`, then
+        `ifft :in-order nil :window (bit-reverse filter)`, renormalised to its input energy and
+        accumulated into a complex destination of len(vector).  One device pipeline, all chunks batched."""
+        vector = real_samplify(vector)
+        filter = real_samplify(filter)
+        chunk = len(filter)
+        if not power_of_two_p(chunk) or chunk < 2:
+            raise NapaFFTError(1, f"filter length {chunk} is not a power of two >= 2")
+        filter_rev = self.bit_reverse(filter)
+        window = self.window_vector(triangle, chunk)
+        dst = np.zeros(len(vector), dtype=np.complex128)
+        self.b.filter_chunks(_ptr(vector), len(vector), _ptr(filter_rev), _ptr(window), chunk, _ptr(dst))
         return dst
 
     def windowed_rfft(self, signal_vector, center, length, window_fn=hann, dst=None, scale=None):

@@ -287,3 +287,32 @@ def c2c_batch(data, n, direction, in_order=True, scale=None, window=None):
     rc = lib().napa_oracle_c2c_batch(_ptr(data), n, batch, direction, int(bool(in_order)), SCALE[scale], _ptr(w), wt)
     assert rc == 0
     return data
+
+
+def filter_chunks(vector, filter):
+    """example.lisp:69-114 (energy, filter-chunks), statement for statement on top of the oracle's
+    bit_reverse / windowed_fft / ifft: the checker for napafft_filter_chunks."""
+    vector = np.asarray(vector, dtype=np.float64)
+    filt = np.asarray(filter, dtype=np.float64)
+    n = len(vector)
+    destination = np.zeros(n, dtype=np.complex128)
+    chunk_size = len(filt)
+    half_size = chunk_size // 2
+    filt_rev = bit_reverse(filt.copy())
+
+    def energy(x):                       # example.lisp:69-79: sequential sum of re^2 + im^2
+        acc = 0.0
+        for v in x:
+            acc += v.real * v.real + v.imag * v.imag
+        return acc
+    for i in range(0, n, half_size):
+        end = min(n, i + chunk_size)
+        chunk = np.zeros(chunk_size, dtype=np.complex128)
+        chunk[:end - i] = vector[i:end]
+        old_energy = energy(chunk)
+        chunk = windowed_fft(chunk, half_size, chunk_size, window_fn="triangle", dst=chunk, in_order=False)
+        chunk = ifft(chunk, dst=chunk, in_order=False, window=filt_rev)
+        new_energy = energy(chunk)
+        scale = 0.5 * np.sqrt(old_energy / new_energy)
+        destination[i:end] += scale * chunk[:end - i]
+    return destination

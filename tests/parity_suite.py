@@ -252,3 +252,33 @@ def check_window_functions(napa):
     assert np.array_equal(napa.window_vector(g, n), O.window_vector("gauss*", n, param=0.5))
     assert napa.window_vector(P.hann, n) is napa.window_vector(P.hann, n)          # cached
     assert np.array_equal(napa.window_vector(P.hann, n, bit_reverse=True), O.window_vector("hann", n, bit_reverse=True))
+
+
+def check_filter_chunks(napa, n, chunk):
+    """example.lisp:81-114: overlap-add streaming filter against the oracle's statement-for-statement version
+    (energies are summed in a different order on the device: agreement to rounding, not bits)."""
+    x = rand_r(900 + n + chunk, n)
+    # a smooth low-pass response over the bins, like the README's filters
+    k = np.minimum(np.arange(chunk), chunk - np.arange(chunk)) / chunk
+    filt = 1.0 / (1.0 + (8 * k) ** 4)
+    got = napa.filter_chunks(x, filt)
+    want = O.filter_chunks(x, filt)
+    assert got.shape == want.shape and got.dtype == np.complex128
+    assert nre(got, want) <= 2 * tol(chunk), (n, chunk, nre(got, want))
+    return nre(got, want)
+
+
+def check_typed_inputs(napa, n):
+    """complex-samplify (support.lisp:64-93) on the device -- real-double, real-single and
+    complex-single inputs give exactly the transform of their widened copy (widening is exact)."""
+    xr = rand_r(700 + n, n)
+    xc = rand_c(701 + n, n)
+    w = rand_r(702 + n, n, 1.0, 2.0)
+    for v in (xr, xr.astype(np.float32), xc.astype(np.complex64)):
+        wide = v.astype(np.complex128)
+        for kw in ({}, {"in_order": False, "scale": "sqrt"}, {"window": w}):
+            assert np.array_equal(napa.fft(v, **kw), napa.fft(wide.copy(), **kw)), (n, v.dtype, kw)
+            assert nre(napa.fft(v, **kw), O.fft(wide.copy(), **kw)) <= tol(n)
+        assert np.array_equal(napa.ifft(v, in_order=False), napa.ifft(wide.copy(), in_order=False))
+        d = np.empty(n + 3, dtype=np.complex128)
+        assert napa.fft(v, dst=d) is d and np.array_equal(d[:n], napa.fft(wide.copy()))

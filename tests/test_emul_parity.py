@@ -137,3 +137,14 @@ def test_three_digit_plans(napa, digits, n, monkeypatch):
         S.check_ifft(napa, n, in_order, True, "complex")
     S.check_layout_bit_exact(napa, n)
     S.check_offsets_exact(napa, n)
+
+
+@pytest.mark.parametrize("n,chunk", [(1000, 64), (4096, 256), (777, 1024), (5000, 2), (3 * 8192 + 5, 16384)])
+def test_filter_chunks(napa, n, chunk):
+    """overlap-add driver (ragged last chunks, signal shorter than a chunk, two-pass chunk size)"""
+    S.check_filter_chunks(napa, n, chunk)
+
+
+@pytest.mark.parametrize("n", [2, 8, 256, 4096, 1 << 14])
+def test_typed_inputs(napa, n):
+    S.check_typed_inputs(napa, n)

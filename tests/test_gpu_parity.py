@@ -195,3 +195,14 @@ def test_optional_l2_pipeline_path_gpu():
         out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "gpu"],
                              env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n,chunk", [(1000, 64), (100000, 1024), (777, 1024), (5000, 2), (1 << 20, 1 << 16), (300001, 4096)])
+def test_filter_chunks(napa, n, chunk):
+    """overlap-add driver of example.lisp:81-114 as one device pipeline"""
+    S.check_filter_chunks(napa, n, chunk)
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 256, 4096, 1 << 14, 1 << 18, 1 << 21])
+def test_typed_inputs(napa, n):
+    S.check_typed_inputs(napa, n)
