@@ -99,3 +99,22 @@
                         (scale-code scale) (if in-order 1 0)
                         (if window (vector-sap window) (int-sap 0)) (window-code window) 0)))
   dst)
+
+
+;;; example.lisp:81-114 -- the overlap-add streaming filter, every chunk in one device batch.
+;;; Same arguments and result as the reference's FILTER-CHUNKS (a complex-sample-array of
+;;; (length vector)); chunk energies are summed on the device, so the result agrees with the
+;;; reference to rounding rather than bit for bit.
+(defun filter-chunks (vector filter)
+  (declare (type real-sample-array vector filter))
+  (let* ((chunk-size  (length filter))
+         (destination (make-array (length vector) :element-type 'complex-sample
+                                                  :initial-element (complex 0d0)))
+         (filter-rev  (bit-reverse filter))
+         (window      (window-vector 'triangle chunk-size)))
+    (sb-sys:with-pinned-objects (vector filter-rev window destination)
+      (napa-fft.b200::check
+       (napa-fft.b200::napafft-filter-chunks (sb-sys:vector-sap vector) (length vector)
+                                              (sb-sys:vector-sap filter-rev) (sb-sys:vector-sap window)
+                                              chunk-size (sb-sys:vector-sap destination))))
+    destination))

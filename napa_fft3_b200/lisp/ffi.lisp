@@ -38,6 +38,15 @@
   (v1 system-area-pointer) (v2 system-area-pointer) (dst system-area-pointer)
   (n size-t) (batch size-t) (scale int))
 
+;; example.lisp:81-114 (filter-chunks) as one device pipeline, and complex-samplify on the device
+(define-alien-routine "napafft_filter_chunks" int
+  (vector system-area-pointer) (len size-t) (filter-rev system-area-pointer) (window system-area-pointer)
+  (chunk size-t) (dst system-area-pointer))
+(define-alien-routine "napafft_c2c_typed" int
+  (src system-area-pointer) (src-type int) (dst system-area-pointer) (n size-t) (batch size-t)
+  (dir int) (scale int) (in-order int) (window system-area-pointer) (window-type int)
+  (window-per-batch int))
+
 (defun check (status)
   (unless (zerop status)
     (error 'napafft-error :status status :message (napafft-last-error)))

@@ -20,7 +20,7 @@
            "RFFT" "RIFFT"
            "WINDOWED-RFFT" "WINDOWED-RIFFT"
            ;; new exports of the B200 build (batched / device-resident paths)
-           "FFT-BATCH" "NAPAFFT-ERROR"))
+           "FFT-BATCH" "FILTER-CHUNKS" "NAPAFFT-ERROR"))
 
 (defpackage "NAPA-FFT.B200"
   (:use "CL" "SB-ALIEN" "SB-SYS" "NAPA-FFT"))
