@@ -216,7 +216,7 @@ template <int K, bool LEAN> static pass_fn pass_kernel_k(int l) {
     return nullptr;
 }
 static pass_fn pass_kernel(int l, int kind, bool lean) {
-    if (l < 7) kind = KIND_COL;            // small L: one lane map (see kind_lm)
+    if (l < 7 && kind != KIND_ROW) kind = KIND_COL;   // small L: one lane map (see kind_lm); KIND_ROW = dense-rows variant
     if (lean) return kind == KIND_COL ? pass_kernel_k<0, true>(l) : (kind == KIND_ROW ? pass_kernel_k<1, true>(l) : pass_kernel_k<2, true>(l));
     return kind == KIND_COL ? pass_kernel_k<0, false>(l) : (kind == KIND_ROW ? pass_kernel_k<1, false>(l) : pass_kernel_k<2, false>(l));
 }
@@ -241,8 +241,14 @@ static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStr
     p.lg_tpi = ilog2((size_t)p.tiles_per_item); p.lg_G = ilog2((size_t)p.G);
     if (ntiles <= 0) return NAPA_OK;
     if (ntiles > 0x7fffffffLL) return fail(NAPA_E_UNSUPPORTED, "grid too large (%lld tiles)", ntiles);
+    if (l < 7) {
+        // dense rows: back-to-back single-pass transforms, read and written as whole contiguous tiles
+        const bool dense = kind == KIND_ROW && (p.flags & napa::PF_Q_IS_BATCH) && p.src_batch_stride == (1LL << l) &&
+                           p.dst_batch_stride == (1LL << l) && !(p.flags & napa::PF_RIFFT_PRE);
+        kind = dense ? KIND_ROW : KIND_COL;
+    }
     pass_fn fn = pass_kernel(l, kind, (p.flags & ~napa::LEAN_FLAGS) == 0);
-    NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::kind_smem_bytes(l, l < 7 ? 0 : kind), st, p);
+    NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::kind_smem_bytes(l, kind), st, p);
     g_launches++;
     return NAPA_OK;
 }

@@ -505,11 +505,15 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 // used ones do not serialise the loads.
 // ALLOWED: the flag bits this instantiation can ever see (the persistent pipeline knows the role of
 // each pass at compile time; masking lets the compiler drop the other fusion paths = smaller code).
+// DENSE (L < 128, single-pass row tiles of back-to-back transforms): the tile is one contiguous block
+// of 2048 points.  With one or a few threads per transform a direct access touches 32 different
+// lines per warp instruction, so the block is instead read and written fully coalesced and
+// transposed through a padded shared-memory image [q][L + 1] (conflict-free both ways).
 // STAGED: the tile's input was bulk-copied into `sm` itself (stage_issue below; rows of C points
 // for a column tile, C rows of L points for a row tile) and its arrival is awaited on `mbar`;
 // the exchange then reuses the same buffer (REUSE must be set).
 template <int LOG2L, bool COHERENT, int LM, int SM_, class Sync, bool REUSE, class Hook, unsigned ALLOWED = 0xffffffffu, bool HINTED = true,
-          bool STAGED = false>
+          bool STAGED = false, bool DENSE = false>
 __device__ __forceinline__ void run_tile(const PassParams &p, const long long tile, cplx *sm,
                                          const long long src_item_delta, const long long dst_item_delta,
                                          const L2Policies &pol, Hook &hook,
@@ -529,6 +533,27 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
     const bool in_reorder = REORDER_OK && LM == MAP_T && (flags & PF_IN_REV);
 
     cplx v[16];
+    constexpr int DPITCH = L + 1;                       // dense image: transform q at sm[q * (L + 1)]
+    long long dense_valid = 0;                           // points of the tile that exist (ragged last tile)
+    if constexpr (DENSE) {
+        constexpr int C = 1 << plan_log2c(LOG2L), NT = plan_threads(LOG2L);
+        static_assert(!STAGED && LM == MAP_Q && SM_ == MAP_Q, "dense rows use the q-fastest lane map");
+        const long long item0 = tile * C;
+        const long long left = p.batch - item0;
+        dense_valid = (left < C ? left : (long long)C) << LOG2L;
+        const cplx *g = p.src + (item0 + src_item_delta) * p.src_batch_stride;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int e = (int)threadIdx.x + NT * j;
+            v[j] = e < dense_valid ? ld_data<COHERENT>(g + e, src_hint, pol) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int e = (int)threadIdx.x + NT * j;
+            sm[(e >> LOG2L) * DPITCH + (e & (L - 1))] = v[j];
+        }
+        Sync::sync();
+    }
     if (c.valid) {
         const cplx *src = p.src + (c.item + src_item_delta) * p.src_batch_stride + s_xoff;
         const long long s_i = p.s_i;
@@ -545,7 +570,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
                 wv[m] = __ldg(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
             }
         }
-        if constexpr (STAGED) {
+        if constexpr (DENSE) {
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = sm[q * DPITCH + lpos(m)];
+        } else if constexpr (STAGED) {
             static_assert(REUSE, "the staging buffer doubles as the exchange buffer");
             constexpr int LC = plan_log2c(LOG2L);
             mbar_wait(mbar, mbar_parity);
@@ -619,7 +647,8 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         if (in_reorder) Stages<LOG2L, 0, 0, PLANAR, true, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
         else Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
     } else {
-        Stages<LOG2L, 0, 0, PLANAR, REUSE, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
+        // DENSE: everyone must have read its points out of the dense image before the first exchange overwrites it
+        Stages<LOG2L, 0, 0, PLANAR, REUSE || DENSE, Sync, Hook>::run(v, sm, p.stage_tw, t, q, d.t, d.q, hook);
     }
 
     const bool out_reorder = REORDER_OK && SM_ == MAP_T && (flags & PF_OUT_REV);
@@ -641,6 +670,21 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             for (int m = 0; m < 16; m++) v[m] = sm[reorder_phys<LOG2L>(d.t + m * T, d.q)];
         }
     }
+    if constexpr (DENSE) {
+        constexpr int C = 1 << plan_log2c(LOG2L), NT = plan_threads(LOG2L);
+        Sync::sync();                                    // the last exchange (or the dense image) has been read
+#pragma unroll
+        for (int m = 0; m < 16; m++)
+            sm[d.q * DPITCH + ((flags & PF_OUT_REV) ? rev_bits(d.t + m * T, LOG2L) : d.t + m * T)] = v[m];
+        Sync::sync();
+        cplx *g = p.dst + (tile * C + dst_item_delta) * p.dst_batch_stride;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int e = (int)threadIdx.x + NT * j;
+            if (e < dense_valid) st_data(g + e, sm[(e >> LOG2L) * DPITCH + (e & (L - 1))], dst_hint, pol);
+        }
+        return;
+    }
     if (d.valid) {
         cplx *dst = p.dst + (d.item + dst_item_delta) * p.dst_batch_stride + d.d_xoff;
         const long long d_i = p.d_i;
@@ -660,8 +704,11 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 // column-like (transposed) store (T,Q).  L < 128 always uses (Q,Q).
 __host__ __device__ constexpr int kind_lm(int l, int kind) { return l >= 7 && kind != 0 ? MAP_T : MAP_Q; }
 __host__ __device__ constexpr int kind_sm(int l, int kind) { return l >= 7 && kind == 1 ? MAP_T : MAP_Q; }
+__host__ __device__ constexpr size_t dense_smem_bytes(int l) { return (size_t)(((1u << l) + 1) << plan_log2c(l)) * sizeof(cplx); }
 __host__ __device__ constexpr size_t kind_smem_bytes(int l, int kind) {
-    return (kind_lm(l, kind) == MAP_Q && kind_sm(l, kind) == MAP_Q) ? plan_smem_bytes(l) : plan_smem_bytes_planar(l);
+    return (kind_lm(l, kind) == MAP_Q && kind_sm(l, kind) == MAP_Q)
+               ? (l < 7 && kind == 1 && dense_smem_bytes(l) > plan_smem_bytes(l) ? dense_smem_bytes(l) : plan_smem_bytes(l))
+               : plan_smem_bytes_planar(l);
 }
 
 // One tile per CTA (single-pass transforms and every pass of multi-pass ones by default).
@@ -674,8 +721,9 @@ fft_pass_kernel(const PassParams p) {
     NAPA_DYN_SMEM(cplx, sm);
     L2Policies pol{};                                 // plain loads/stores: no L2 policy operands
     NoHook nh;
-    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND), SyncAll, false, NoHook, LEAN ? LEAN_FLAGS : 0xffffffffu, false>(
-        p, (long long)blockIdx.x, sm, 0, 0, pol, nh);
+    // L < 128: KIND 1 selects the dense-rows variant (single-pass batches of back-to-back transforms)
+    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND), SyncAll, false, NoHook, LEAN ? LEAN_FLAGS : 0xffffffffu, false,
+             false, (LOG2L < 7 && KIND == 1)>(p, (long long)blockIdx.x, sm, 0, 0, pol, nh);
 }
 
 // ------------------------------------------------------------------------------------------

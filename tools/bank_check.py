@@ -108,8 +108,35 @@ def check_reorder(l):
     return worst
 
 
+def check_dense(l):
+    """dense-rows image [q][L + 1] of the L < 128 single-pass kernels: coalesced side (thread e -> element e)
+    and transform side (lane map Q, position t + m*T, natural or bit-reversed)"""
+    L, T, C = 1 << l, 1 << (l - 4), 1 << (log2pts(l) - l)
+    worst_c = worst_t = 0
+    tot_c = n_c = 0
+    for w0 in range(0, 128, 32):
+        for j in range(16):
+            addrs = [((w0 + i + 128 * j) >> l) * (L + 1) + ((w0 + i + 128 * j) & (L - 1)) for i in range(32)]
+            wf = wavefronts(addrs)
+            worst_c = max(worst_c, wf); tot_c += wf; n_c += 1
+        for m in range(16):
+            for bitrev in (False, True):
+                addrs = []
+                for tid in range(w0, w0 + 32):
+                    t, q = ids(tid, l, "Q")
+                    pos = t + m * T
+                    addrs.append(q * (L + 1) + (rev(pos, l) if bitrev else pos))
+                worst_t = max(worst_t, wavefronts(addrs))
+    return worst_c, tot_c / n_c, worst_t
+
+
 if __name__ == "__main__":
     bad = 0
+    for l in (4, 5, 6):
+        wc, avg, wt = check_dense(l)
+        flag = "" if wt == 4 and avg < 4.6 else "   <-- CONFLICT"
+        bad += flag != ""
+        print("L=2^%-2d dense-rows image: coalesced side %.2f wavefronts/instr on average (worst %d, rows straddled), transform side %d (ideal 4)%s" % (l, avg, wc, wt, flag))
     for l in range(5, 14):
         for lm, sm in (("Q", "Q"), ("T", "T"), ("T", "Q")):
             w, r = check(l, lm, sm)
