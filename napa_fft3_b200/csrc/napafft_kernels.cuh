@@ -161,6 +161,7 @@ enum : unsigned {
     PF_WIN_REV    = 1u << 9,   // window index = rev_{lgN}(offset in transform) (ifft :in-order t)
     PF_SCALE      = 1u << 10,
     PF_RIFFT_PRE  = 1u << 11,  // x = (a+b) + (a-b)*r2tw[off], b = src[off + N]   (real.lisp:170-177)
+    PF_RFFT_POST  = 1u << 12,  // single-pass row tiles: rfft epilogue (real.lisp:16-30, 128-134) fused into the store
 };
 
 struct PassParams {
@@ -668,6 +669,39 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             Sync::sync();
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = sm[reorder_phys<LOG2L>(d.t + m * T, d.q)];
+        }
+    }
+    if constexpr (LOG2L >= 7 && SM_ == MAP_T) {
+        if (flags & PF_RFFT_POST) {
+            // Z = FFT_L(packed reals) is complete inside the tile (q = one transform).  Each thread
+            // finishes its own bins i: X[i] = E_i + O_i w^i, X[i + L] = E_i - O_i w^i with
+            // O_i = (conj(swap Z_i) + swap Z_{L-i}) / 2, E_i = Z_i - i O_i, the partner Z_{L-i}
+            // fetched from a planar image of the outputs; same operations, in the same order, as
+            // rfft_post_kernel, so the bits do not depend on which path ran.
+            Sync::sync();                                // the last exchange has been read
+#pragma unroll
+            for (int m = 0; m < 16; m++) sm[(d.q << LOG2L) + d.t + m * T] = v[m];
+            Sync::sync();
+            if (d.valid) {
+                cplx *dst = p.dst + (d.item + dst_item_delta) * p.dst_batch_stride + d.d_xoff;
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const int i = d.t + m * T;
+                    const cplx x = v[m];
+                    if (i == 0) {
+                        st_data(dst, make_double2(x.x + x.y, 0.0), dst_hint, pol);
+                        st_data(dst + L, make_double2(x.x - x.y, 0.0), dst_hint, pol);
+                    } else {
+                        const cplx y = sm[(d.q << LOG2L) + (L - i)];
+                        const cplx oi = make_double2(0.5 * (x.y + y.y), 0.5 * (y.x - x.x));
+                        const cplx ei = make_double2(x.x + oi.y, x.y - oi.x);
+                        const cplx ti = cmul(oi, ldg_c(p.r2tw + i));
+                        st_data(dst + i, cadd(ei, ti), dst_hint, pol);
+                        st_data(dst + i + L, csub(ei, ti), dst_hint, pol);
+                    }
+                }
+            }
+            return;
         }
     }
     if constexpr (DENSE) {

@@ -206,3 +206,16 @@ def test_filter_chunks(napa, n, chunk):
 @pytest.mark.parametrize("n", [1, 2, 8, 256, 4096, 1 << 14, 1 << 18, 1 << 21])
 def test_typed_inputs(napa, n):
     S.check_typed_inputs(napa, n)
+
+
+@pytest.mark.parametrize("n", [256, 1 << 11, 1 << 14])
+def test_rfft_fused_epilogue_matches_unfused(napa, n, monkeypatch):
+    """the single-launch rfft (epilogue fused into the half-size transform's store) against the two-launch path"""
+    from oracle import napa_oracle as O
+    x = np.stack([S.rand_r(40 + i, n) for i in range(9)])
+    fused = napa.rfft_batch(x.copy())
+    monkeypatch.setenv("NAPAFFT_RFFT_UNFUSED", "1")
+    unfused = napa.rfft_batch(x.copy())
+    assert S.nre(fused, unfused) <= 1e-15
+    for i in (0, 8):
+        assert S.nre(fused[i], O.rfft(x[i])) <= S.tol(n)
