@@ -78,6 +78,7 @@ struct State {
     void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = (size_t)1 << 30; // items per launch of the multi-launch path (also the natural-order scratch size)
     void *oa_buf = nullptr; size_t oa_bytes = 0;   // chunk matrix + energies of the overlap-add filter
+    size_t max_scratch_bytes = (size_t)16 << 30;   // natural-order scratch copy up to this size, else in-place fallback
     size_t pipe_l2_bytes = 40u << 20;     // live intermediate of the group-fused kernel (groups * n * 16 B)
     int pipe_gsize = 0;                   // CTAs per group (0 = auto)
     bool use_pipeline = false;            // persistent L2 pipeline: measured slower than two plain launches
@@ -591,7 +592,11 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         CU(cudaGetLastError());
         return NAPA_OK;
     }
-    if (natural) {
+    // Natural order normally goes through a scratch copy of one chunk; a single transform too large for
+    // that (> max_scratch_bytes, 2^31 and up by default) falls back to the in-place bit-reversed
+    // pipeline plus the in-place bit-reversal pass, which needs no extra memory.
+    const bool nat_scratch = natural && chunk * n * sizeof(cplx) <= G.max_scratch_bytes;
+    if (nat_scratch) {
         // natural in -> natural out, one HBM pass per digit and no separate bit-reversal pass:
         //   p == 2: column pass src -> scratch [k1][n2], row pass scratch -> dst stored transposed (k1 + L1 k2)
         //   p == 3: column pass src -> dst [k1][n2][n3]; column pass dst -> scratch [k2][k1][n3]; row pass
@@ -640,6 +645,11 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     }
 
     // bit-reversed pipelines (in place on dst after the first pass), any number of digits
+    if (natural && inv) {
+        // reference order: bit-reverse first, then DIT (easy-interface.lisp:83-95)
+        OK(exec_bitrev(src, dst, n, batch, sstride, dstride, NAPA_ELT_COMPLEX, st));
+        src = dst; sstride = dstride;
+    }
     for (size_t b0 = 0; b0 < batch; b0 += chunk) {
         const size_t nb = std::min(chunk, batch - b0);
         for (int step = 0; step < p; step++) {
@@ -669,6 +679,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             OK(launch_pass(d[s], lgB > 0 ? KIND_COL : KIND_ROW, pp, tpi * (long long)nb, st));
         }
     }
+    if (natural && !inv) OK(exec_bitrev(dst, dst, n, batch, dstride, dstride, NAPA_ELT_COMPLEX, st));
     CU(cudaGetLastError());
     return NAPA_OK;
 }
@@ -1053,6 +1064,7 @@ NAPA_API int napafft_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(NAPA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
+    if (const char *env = getenv("NAPAFFT_MAX_SCRATCH_KB")) G.max_scratch_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_L2_MB")) G.pipe_l2_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_PIPE_GSIZE")) G.pipe_gsize = atoi(env);
     if (const char *env = getenv("NAPAFFT_PIPELINE")) G.use_pipeline = atoi(env) != 0;

@@ -148,3 +148,14 @@ def test_filter_chunks(napa, n, chunk):
 @pytest.mark.parametrize("n", [2, 8, 256, 4096, 1 << 14])
 def test_typed_inputs(napa, n):
     S.check_typed_inputs(napa, n)
+
+
+def test_natural_order_in_place_fallback():
+    """single transforms too large for a scratch copy (2^31 and up by default) take the in-place
+    bit-reversed pipeline + bit-reversal pass; forced here at small sizes with NAPAFFT_MAX_SCRATCH_KB"""
+    import subprocess
+    env = dict(os.environ, NAPAFFT_MAX_SCRATCH_KB="1")
+    env.pop("NAPAFFT_PIPELINE", None)
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
