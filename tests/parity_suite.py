@@ -282,3 +282,32 @@ def check_typed_inputs(napa, n):
         assert np.array_equal(napa.ifft(v, in_order=False), napa.ifft(wide.copy(), in_order=False))
         d = np.empty(n + 3, dtype=np.complex128)
         assert napa.fft(v, dst=d) is d and np.array_equal(d[:n], napa.fft(wide.copy()))
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_vectors.npz")
+
+
+def check_golden(napa, exact=False):
+    """the committed fixtures of tests/golden/make_golden.py (outputs of the pinned oracle).  exact=True is
+    for the oracle itself (must reproduce its own fixtures bit for bit); the CUDA path is held to the FP64
+    tolerance, bit-exact for the permutations."""
+    g = np.load(GOLDEN)
+    sizes = sorted({int(k.split("_")[0][1:]) for k in g.files if k.startswith("n")})
+    cmp = (lambda a, b, n: np.array_equal(a, b)) if exact else (lambda a, b, n: nre(a, b) <= tol(n))
+    for n in sizes:
+        k = "n%d_" % n
+        xc, xr, wr = g[k + "xc"], g[k + "xr"], g[k + "wr"]
+        assert cmp(napa.fft(xc.copy()), g[k + "fft"], n), (n, "fft")
+        assert cmp(napa.fft(xc.copy(), in_order=False, scale="sqrt", window=wr), g[k + "fft_rev_sqrt_wr"], n), (n, "fft rev")
+        if k + "wc" not in g.files:
+            continue
+        wc = g[k + "wc"]
+        assert cmp(napa.ifft(xc.copy(), in_order=False, scale=True, window=wc), g[k + "ifft_rev_wc"], n), (n, "ifft rev")
+        assert cmp(napa.ifft(xc.copy(), in_order=True, scale="sqrt", window=wr), g[k + "ifft_nat_wr"], n), (n, "ifft nat")
+        assert np.array_equal(napa.bit_reverse(xc.copy()), g[k + "bitrev_c"]), (n, "bit-reverse complex")
+        assert np.array_equal(napa.bit_reverse(xr.copy()), g[k + "bitrev_r"]), (n, "bit-reverse real")
+        assert cmp(napa.rfft(xr.copy()), g[k + "rfft"], n), (n, "rfft")
+        assert cmp(napa.rifft(napa.rfft(xr.copy()), scale=True), g[k + "rifft"], n), (n, "rifft")
+        assert cmp(napa.two_rfft(xr.copy(), wr.copy()), g[k + "2rfft"], n), (n, "%2rfft")
+    got = napa.filter_chunks(g["oa_signal"], g["oa_filter"])
+    assert (np.array_equal(got, g["oa_out"]) if exact else nre(got, g["oa_out"]) <= 2 * tol(64)), "filter-chunks"

@@ -159,3 +159,8 @@ def test_natural_order_in_place_fallback():
     out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_golden_vectors(napa):
+    """shipped csrc (emulated) against the committed oracle fixtures"""
+    S.check_golden(napa)

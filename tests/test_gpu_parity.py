@@ -219,3 +219,8 @@ def test_rfft_fused_epilogue_matches_unfused(napa, n, monkeypatch):
     assert S.nre(fused, unfused) <= 1e-15
     for i in (0, 8):
         assert S.nre(fused[i], O.rfft(x[i])) <= S.tol(n)
+
+
+def test_golden_vectors(napa):
+    """CUDA path through the C ABI against the committed oracle fixtures (tests/golden/)"""
+    S.check_golden(napa)

@@ -134,3 +134,12 @@ def test_size_keeps_tail(oracle):
     assert np.allclose(out[:16], np.fft.fft(x[:16]))
     same = oracle.fft(x, dst=x, size=16)
     assert same is x
+
+
+def test_golden_vectors_reproduce(oracle):
+    """the oracle still reproduces tests/golden/oracle_vectors.npz bit for bit (fixture drift guard:
+    compiler flags, libm, edits to oracle/)"""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity_suite as S
+    S.check_golden(oracle, exact=True)
