@@ -69,7 +69,7 @@ struct State {
     std::map<int, BigTw> big;                        // by log2 M
     std::map<std::pair<size_t, int>, cplx *> r2tw;   // (n, dir) -> n/2 entries (reference recurrence)
     std::map<int, PairTable> pairs;                  // bit-reversal tile pairs by width
-    cplx *scratch = nullptr; size_t scratch_bytes = 0;
+    std::map<cudaStream_t, std::pair<cplx *, size_t>> scratch;   // natural-order intermediate, one per stream
     // staging for host-pointer calls
     cudaStream_t stream[2] = {};
     cudaEvent_t done[2] = {};
@@ -77,7 +77,7 @@ struct State {
     void *dbuf[2] = {}; size_t dbuf_bytes = 0;
     void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = (size_t)1 << 30; // items per launch of the multi-launch path (also the natural-order scratch size)
-    void *oa_buf = nullptr; size_t oa_bytes = 0;   // chunk matrix + energies of the overlap-add filter
+    std::map<cudaStream_t, std::pair<cplx *, size_t>> oa_buf;    // chunk matrix + energies of the overlap-add filter, one per stream
     size_t max_scratch_bytes = (size_t)16 << 30;   // natural-order scratch copy up to this size, else in-place fallback
     size_t pipe_l2_bytes = 40u << 20;     // live intermediate of the group-fused kernel (groups * n * 16 B)
     int pipe_gsize = 0;                   // CTAs per group (0 = auto)
@@ -187,11 +187,16 @@ static int ensure_r2tw(size_t n, int dir, cplx **out) {
     return NAPA_OK;
 }
 
-static int ensure_scratch(size_t bytes) {
-    if (G.scratch_bytes >= bytes) return NAPA_OK;
-    if (G.scratch) { CU(cudaDeviceSynchronize()); CU(cudaFree(G.scratch)); G.scratch = nullptr; G.scratch_bytes = 0; }
-    CU(cudaMalloc(&G.scratch, bytes));
-    G.scratch_bytes = bytes;
+// One scratch area PER STREAM: launches queued on different streams (the two staging streams of the
+// host-pointer entry points, or a caller's own streams) run concurrently and must not share it.
+static int ensure_scratch(cudaStream_t st, size_t bytes, cplx **out) {
+    auto &slot = G.scratch[st];
+    if (slot.second < bytes) {
+        if (slot.first) { CU(cudaDeviceSynchronize()); CU(cudaFree(slot.first)); slot.first = nullptr; slot.second = 0; }
+        CU(cudaMalloc((void **)&slot.first, bytes));
+        slot.second = bytes;
+    }
+    *out = slot.first;
     return NAPA_OK;
 }
 
@@ -544,17 +549,17 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         long long tpi;
         if (natural) {
             // A: column pass src -> the group's scratch slot (+ inter-pass twiddle); B: row pass slot -> dst, transposed store
-            OK(ensure_scratch((size_t)pp.ngroups * n * sizeof(cplx)));
+            cplx *scratch; OK(ensure_scratch(st, (size_t)pp.ngroups * n * sizeof(cplx), &scratch));
             BigTw bt; OK(ensure_big_tw(lg, &bt));
             PassParams &p1 = pp.a, &p2 = pp.b;
             pass_geometry(d, 0, p1, &tpi);
-            p1.src = src; p1.dst = G.scratch;
+            p1.src = src; p1.dst = scratch;
             p1.src_batch_stride = (long long)sstride; p1.dst_batch_stride = (long long)n; p1.batch = (long long)batch;
             p1.flags = napa::PF_TW_STORE | (inv ? napa::PF_CONJ_IN : 0);
             p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << lg) - 1;
             first_pass_fusions(p1, o, n, win_rev);
             pass_geometry(d, 1, p2, &tpi);
-            p2.src = G.scratch; p2.dst = dst;
+            p2.src = scratch; p2.dst = dst;
             p2.src_batch_stride = (long long)n; p2.dst_batch_stride = (long long)dstride; p2.batch = (long long)batch;
             p2.flags = inv ? napa::PF_CONJ_OUT : 0;
             p2.d_SA = 1LL << napa::plan_log2c(d[1]); p2.d_SG = 0; p2.d_i = 1LL << d[0]; p2.d_q = 1;
@@ -603,7 +608,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         //           scratch -> dst stored transposed ((k1 + L1 k2) + L1 L2 k3)
         // The inverse runs the same forward structure between conjugations (bitwise the DIT result of
         // the bit-reversed input up to the order of additions; window index = rev(k), set by win_rev).
-        OK(ensure_scratch(chunk * n * sizeof(cplx)));
+        cplx *scratch; OK(ensure_scratch(st, chunk * n * sizeof(cplx), &scratch));
         for (size_t b0 = 0; b0 < batch; b0 += chunk) {
             const size_t nb = std::min(chunk, batch - b0);
             long long tpi;
@@ -615,7 +620,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                 PassParams p1{};
                 pass_geometry(d, s, p1, &tpi);
                 const bool to_scratch = s == p - 2;
-                p1.src = cur; p1.dst = to_scratch ? G.scratch : dst + b0 * dstride;
+                p1.src = cur; p1.dst = to_scratch ? scratch : dst + b0 * dstride;
                 p1.src_batch_stride = cur_stride; p1.dst_batch_stride = (long long)(to_scratch ? n : dstride); p1.batch = (long long)nb;
                 BigTw bt; OK(ensure_big_tw(d[s] + lgB, &bt));
                 p1.flags = napa::PF_TW_STORE | ((inv && s == 0) ? napa::PF_CONJ_IN : 0);
@@ -633,7 +638,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             }
             PassParams p2{};
             pass_geometry(d, p - 1, p2, &tpi);
-            p2.src = G.scratch; p2.dst = dst + b0 * dstride;
+            p2.src = scratch; p2.dst = dst + b0 * dstride;
             p2.src_batch_stride = (long long)n; p2.dst_batch_stride = (long long)dstride; p2.batch = (long long)nb;
             p2.flags = inv ? napa::PF_CONJ_OUT : 0;
             // row r = ra*C + q holds the leading output digits (k1 + L1 k2); output k_last -> address r + (n / L_last) * k_last
@@ -727,7 +732,7 @@ static int exec_cols(const cplx *src, cplx *dst, size_t n1, size_t cols, int dir
     // Inverse (DIT, mirror): digit b first (input rows k1 = ka + La*kb), then digit a.
     const int la = d[0], lb = d[1];
     const long long La = 1LL << la, Lb = 1LL << lb;
-    OK(ensure_scratch(n1 * cols * sizeof(cplx)));
+    cplx *scratch; OK(ensure_scratch(st, n1 * cols * sizeof(cplx), &scratch));
     BigTw it; OK(ensure_big_tw(lg1, &it));
     PassParams pa{}, pb{};
     // digit a over the [La][Lb*B] view, intra twiddle W_n1^{ka * jb}, jb = col / B
@@ -749,21 +754,21 @@ static int exec_cols(const cplx *src, cplx *dst, size_t n1, size_t cols, int dir
         pb.tw_mul_t = 1;
     }
     if (!inv) {
-        pa.src = src; pa.dst = G.scratch; pa.flags |= napa::PF_TW_STORE;
+        pa.src = src; pa.dst = scratch; pa.flags |= napa::PF_TW_STORE;
         if (scale != 1.0) { pa.flags |= napa::PF_SCALE; pa.scale = scale; }
-        pb.src = G.scratch; pb.dst = dst;
+        pb.src = scratch; pb.dst = dst;
         pb.d_SA = B; pb.d_i = La * B;                       // store row ka + La*kb
         if (lgM > 0) global_tw(pb, La, 1);                   // k1 = ra + La*(t + m*T)
         OK(launch_pass(la, KIND_COL, pa, pa.tiles_per_item, st));
         OK(launch_pass(lb, KIND_COL, pb, pb.tiles_per_item, st));
     } else {
         // DIT mirror: first the b digit, reading rows k1 = ka + La*kb, global twiddle on its load
-        pb.src = src; pb.dst = G.scratch;
+        pb.src = src; pb.dst = scratch;
         pb.s_SA = B; pb.s_i = La * B;
         pb.flags |= napa::PF_CONJ_IN;
         if (scale != 1.0) { pb.flags |= napa::PF_SCALE; pb.scale = scale; }
         if (lgM > 0) global_tw(pb, La, 1);
-        pa.src = G.scratch; pa.dst = dst; pa.flags |= napa::PF_TW_LOAD | napa::PF_CONJ_OUT;
+        pa.src = scratch; pa.dst = dst; pa.flags |= napa::PF_TW_LOAD | napa::PF_CONJ_OUT;
         OK(launch_pass(lb, KIND_COL, pb, pb.tiles_per_item, st));
         OK(launch_pass(la, KIND_COL, pa, pa.tiles_per_item, st));
     }
@@ -881,14 +886,13 @@ static int exec_filter_chunks(const double *vec, size_t len, const double *filte
     const int lgc = ilog2(chunk);
     const size_t half = chunk / 2, nchunks = (len + half - 1) / half;
     const size_t need = nchunks * chunk * sizeof(cplx) + 2 * nchunks * sizeof(double) + 256;
-    if (G.oa_bytes < need) {
-        CU(cudaDeviceSynchronize());
-        if (G.oa_buf) CU(cudaFree(G.oa_buf));
-        G.oa_buf = nullptr; G.oa_bytes = 0;
-        CU(cudaMalloc(&G.oa_buf, need));
-        G.oa_bytes = need;
+    auto &oa = G.oa_buf[st];
+    if (oa.second < need) {
+        if (oa.first) { CU(cudaDeviceSynchronize()); CU(cudaFree(oa.first)); oa.first = nullptr; oa.second = 0; }
+        CU(cudaMalloc((void **)&oa.first, need));
+        oa.second = need;
     }
-    cplx *X = (cplx *)G.oa_buf;
+    cplx *X = oa.first;
     double *e_old = (double *)(X + nchunks * chunk), *e_new = e_old + nchunks;
     NAPA_LAUNCH(napa::oa_gather_kernel, (unsigned)nchunks, 256, 0, st, vec, (long long)len, X, e_old, lgc);
     g_launches++;
@@ -1085,9 +1089,10 @@ NAPA_API int napafft_shutdown(void) {
     G.r2tw.clear();
     for (auto &kv : G.pairs) cudaFree(kv.second.dev);
     G.pairs.clear();
-    if (G.scratch) cudaFree(G.scratch);
-    if (G.oa_buf) { cudaFree(G.oa_buf); G.oa_buf = nullptr; G.oa_bytes = 0; }
-    G.scratch = nullptr; G.scratch_bytes = 0;
+    for (auto &kv : G.scratch) cudaFree(kv.second.first);
+    G.scratch.clear();
+    for (auto &kv : G.oa_buf) cudaFree(kv.second.first);
+    G.oa_buf.clear();
     for (auto &kv : G.counters) cudaFree(kv.second.first);
     G.counters.clear();
     if (G.h_error) { cudaFreeHost(G.h_error); G.h_error = nullptr; G.d_error = nullptr; }

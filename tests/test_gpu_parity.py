@@ -224,3 +224,20 @@ def test_rfft_fused_epilogue_matches_unfused(napa, n, monkeypatch):
 def test_golden_vectors(napa):
     """CUDA path through the C ABI against the committed oracle fixtures (tests/golden/)"""
     S.check_golden(napa)
+
+
+@pytest.mark.parametrize("lg", [14, 16])
+def test_host_batches_across_staging_chunks(napa, lg, monkeypatch):
+    """natural-order multi-pass transforms staged over both copy streams: each stream has its own
+    scratch, chunks in flight on the two streams must not disturb each other"""
+    from oracle import napa_oracle as O
+    monkeypatch.setenv("NAPAFFT_STAGE_MB", "8")
+    n, batch = 1 << lg, (200 if lg == 14 else 60)
+    rng = np.random.Generator(np.random.Philox(lg))
+    x = rng.uniform(-1, 1, (batch, n)) + 1j * rng.uniform(-1, 1, (batch, n))
+    for rep in range(3):
+        got = napa.fft_batch(x.copy())
+        for i in range(0, batch, 7):
+            assert S.nre(got[i], O.fft(x[i])) <= S.tol(n), (lg, rep, i)
+        back = napa.fft_batch(got, direction=-1, scale=True)
+        assert S.nre(back, x) <= S.tol(n), (lg, rep)
