@@ -591,12 +591,22 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         }
         if (flags & PF_RIFFT_PRE) {
             // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177)
+            // partner and twiddle loads in batches of four (a 512-thread tile has no registers for more):
+            // four exposed latencies instead of one per element
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const long long off = s_xoff + (long long)lpos(m) * s_i;
-                const cplx y = ld_data<COHERENT>(src - s_xoff + off + p.aux_off, src_hint, pol);
-                const cplx w = ldg_c(p.r2tw + off);
-                v[m] = cadd(cadd(v[m], y), cmul(csub(v[m], y), w));
+            for (int g4 = 0; g4 < 4; g4++) {
+                cplx y[4], w[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const long long off = s_xoff + (long long)lpos(4 * g4 + j) * s_i;
+                    y[j] = ld_data<COHERENT>(src - s_xoff + off + p.aux_off, src_hint, pol);
+                    w[j] = ldg_c(p.r2tw + off);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int m = 4 * g4 + j;
+                    v[m] = cadd(cadd(v[m], y[j]), cmul(csub(v[m], y[j]), w[j]));
+                }
             }
         }
         if (flags & PF_SCALE) {
