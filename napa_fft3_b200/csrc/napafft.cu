@@ -81,10 +81,10 @@ struct State {
     size_t max_scratch_bytes = (size_t)16 << 30;   // natural-order scratch copy up to this size, else in-place fallback
     size_t pipe_l2_bytes = 40u << 20;     // live intermediate of the group-fused kernel (groups * n * 16 B)
     int pipe_gsize = 0;                   // CTAs per group (0 = auto)
-    bool use_pipeline = false;            // persistent L2 pipeline: measured slower than two plain launches
+    bool use_pipeline = false;            // group-fused two-pass kernel: ties with two plain launches today
     bool attrs_set = false;
     int num_sms = 148;
-    std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream ticket/done block
+    std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream group-barrier counters
     int *h_error = nullptr, *d_error = nullptr;                             // mapped error flag
 };
 static State G;
@@ -259,7 +259,7 @@ static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStr
     return NAPA_OK;
 }
 
-// persistent two-pass pipeline kernels: (first-executed digit, second digit, pipeline kind)
+// group-fused two-pass kernels: (first-executed digit, second digit, plan kind)
 typedef void (*pipe_fn)(const napa::PipeParams);
 #ifndef NAPA_EMULATE
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,

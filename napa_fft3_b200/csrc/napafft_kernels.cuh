@@ -499,12 +499,12 @@ __device__ __forceinline__ TileCtx tile_ctx(const PassParams &p, const long long
 
 // One tile of one digit pass.
 //   COHERENT: L2-only (ld.global.cg) data loads, required when another SM wrote the data earlier
-//             in the SAME launch (persistent pipeline): a stale L1 line would be a bug.
+//             in the SAME launch (group-fused kernel): a stale L1 line would be a bug.
 //   LM / SM_: lane maps of the load side and of the store side.
 // All 16 data loads of a thread are issued back to back into v[], and every optional fusion is a
 // separate warp-uniform branch over the whole register array, so unused fusions cost nothing and
 // used ones do not serialise the loads.
-// ALLOWED: the flag bits this instantiation can ever see (the persistent pipeline knows the role of
+// ALLOWED: the flag bits this instantiation can ever see (the group-fused kernel knows the role of
 // each pass at compile time; masking lets the compiler drop the other fusion paths = smaller code).
 // DENSE (L < 128, single-pass row tiles of back-to-back transforms): the tile is one contiguous block
 // of 2048 points.  With one or a few threads per transform a direct access touches 32 different

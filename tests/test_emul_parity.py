@@ -102,8 +102,8 @@ def test_batch_and_stride(napa):
 
 
 @pytest.mark.parametrize("n,batch", [(256, 300), (1024, 70), (4096, 17), (8192, 9), (64, 1100)])
-def test_persistent_single_pass(napa, n, batch):
-    """enough tiles that the launch goes persistent (cp.async-prefetched tile loop), incl. a ragged
+def test_many_tiles_single_pass(napa, n, batch):
+    """many tiles per launch, incl. a ragged
     last tile, the bit-reversed load path and a fused window"""
     from oracle import napa_oracle as O
     x = np.stack([S.rand_c(500 + i, n) for i in range(batch)])
@@ -118,10 +118,12 @@ def test_persistent_single_pass(napa, n, batch):
 
 
 def test_optional_l2_pipeline_path():
-    """the persistent two-pass pipeline (off by default, NAPAFFT_PIPELINE=1) stays correct:
-    several chunks, ring-slot reuse, natural and bit-reversed pipelines"""
+    """the group-fused two-pass kernel (off by default, NAPAFFT_PIPELINE=1) stays correct:
+    scratch-slot reuse across a group's transforms, staged tiles, natural and bit-reversed plans (the emulator
+    runs CTAs one after the other, so groups are one CTA wide here; the group barrier itself is exercised by
+    tests/test_gpu_parity.py on a B200)"""
     import subprocess
-    env = dict(os.environ, NAPAFFT_PIPELINE="1", NAPAFFT_PIPE_CHUNK_KB="256")
+    env = dict(os.environ, NAPAFFT_PIPELINE="1")
     out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
