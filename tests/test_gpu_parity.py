@@ -189,8 +189,10 @@ def test_distributed_building_blocks_single_rank(napa, lgN):
 
 
 def test_optional_l2_pipeline_path_gpu():
+    """group-fused two-pass kernel (NAPAFFT_PIPELINE=1): automatic group shape, narrow groups (several tiles
+    per CTA and phase: the staged prefetch chain) and wide groups (one tile per CTA and phase)"""
     import subprocess
-    for extra in ({}, {"NAPAFFT_PIPE_CHUNK_KB": "4096"}):
+    for extra in ({}, {"NAPAFFT_PIPE_GSIZE": "4"}, {"NAPAFFT_PIPE_GSIZE": "32", "NAPAFFT_PIPE_L2_MB": "8"}):
         env = dict(os.environ, NAPAFFT_PIPELINE="1", **extra)
         out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "gpu"],
                              env=env, capture_output=True, text=True, timeout=600)
