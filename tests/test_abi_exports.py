@@ -83,3 +83,22 @@ def test_argument_errors_via_emulated_abi():
     assert np.array_equal(tw, O.radix2_twiddle(1024, -1.0))                     # real.lisp:53-64 bit-exact
     b.radix2_twiddle(1024, 1, C.c_void_p(tw.ctypes.data))
     assert np.array_equal(tw, O.radix2_twiddle(1024, 1.0))
+
+
+def test_example_helpers(tmp_path):
+    """example.lisp:1-79 host helpers: raw s32 files round-trip with the reference's scaling rules"""
+    import numpy as np
+    from napa_fft3_b200 import examples as E
+    x = np.array([0.0, 0.5, -0.5, 0.999, -1.0, 1e-10])
+    f = E.emit_raw32_file(str(tmp_path / "a.raw"), x)
+    raw = np.fromfile(f, dtype=np.int32)
+    assert list(raw) == [int(np.floor(v * (2**31 - 1))) for v in x]
+    back = E.read_raw32_file(f)
+    assert np.array_equal(back, raw * 2.0 ** -31) and np.max(np.abs(back - x)) < 2.0 ** -30
+    assert np.array_equal(E.read_raw32_file(f, 3), back[:3])
+    assert np.array_equal(E.impulse([1, 3], 4, 2), np.array([0, 2, 0, 2], dtype=complex))
+    v = np.array([1 + 0j, -3j, 0.5, 2])
+    assert np.array_equal(E.amplitude_clamp_fraction(v, 0.5), np.array([0, -3j, 0, 2]))
+    assert np.array_equal(E.amplitude_clamp_k(v, 2), np.array([0, -3j, 0, 2]))
+    assert E.energy(v) == 1 + 9 + 0.25 + 4
+    assert np.array_equal(E.m_plus([1, 2], [3, 4]), np.array([2, 3], dtype=complex))
