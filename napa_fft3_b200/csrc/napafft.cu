@@ -803,9 +803,12 @@ static int exec_bitrev_t(const E *src, E *dst, size_t n, size_t batch, size_t ss
     const int w = ilog2(n);
     if (batch == 0) return NAPA_OK;
     if (w <= 10) {
-        if (batch > 0x7fffffffULL) return fail(NAPA_E_UNSUPPORTED, "batch too large");
+        const int per_cta = (int)std::max<size_t>(1, 2048 / n);          // 2048 elements (<= 32 KiB) per CTA
+        const size_t ctas = (batch + per_cta - 1) / per_cta;
+        if (ctas > 0x7fffffffULL) return fail(NAPA_E_UNSUPPORTED, "batch too large");
         auto k = napa::bitrev_small_kernel<E>;
-        NAPA_LAUNCH(k, (unsigned)batch, 256, n * sizeof(E), st, src, dst, w, (long long)sstride, (long long)dstride);
+        NAPA_LAUNCH(k, (unsigned)ctas, 256, (size_t)per_cta * (n >= 32 ? n / 32 * 33 : n) * sizeof(E), st, src, dst, w, (long long)sstride, (long long)dstride,
+                    (long long)batch, per_cta);
     } else {
         PairTable pt; OK(ensure_pairs(w, &pt));
         long long blocks = (long long)pt.count * (long long)batch;

@@ -1057,19 +1057,26 @@ __global__ void __launch_bounds__(256) bitrev_tiled_kernel(const E *src, E *dst,
     }
 }
 
-// small sizes: one CTA per item, whole vector through shared memory (n <= 2048 elements)
+// small sizes (n <= 1024 elements): a CTA takes `per_cta` items (2048 elements) through shared memory.
+// An item is stored as rows of 32 elements with a pitch of 33, so that the bit-reversed gather
+// (lane stride n/32 elements) spreads over the banks instead of hitting one.
 template <typename E>
 __global__ void __launch_bounds__(256) bitrev_small_kernel(const E *src, E *dst, int w, long long src_stride,
-                                                           long long dst_stride) {
+                                                           long long dst_stride, long long batch, int per_cta) {
     NAPA_DYN_SMEM(E, sm);
     const int n = 1 << w;
-    const E *s = src + (long long)blockIdx.x * src_stride;
-    E *d = dst + (long long)blockIdx.x * dst_stride;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = s[i];
+    const int item_pitch = n >= 32 ? (n >> 5) * 33 : n;          // whole rows only; shorter items are packed
+    const long long item0 = (long long)blockIdx.x * per_cta;
+    const int items = (int)(batch - item0 < per_cta ? batch - item0 : per_cta);
+    const int total = items << w;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int it = e >> w, i = e & (n - 1);
+        sm[it * item_pitch + (i >> 5) * 33 + (i & 31)] = src[(item0 + it) * src_stride + i];
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int r = rev_bits(i, w);
-        d[i] = sm[r];
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int it = e >> w, i = e & (n - 1), r = rev_bits(i, w);
+        dst[(item0 + it) * dst_stride + i] = sm[it * item_pitch + (r >> 5) * 33 + (r & 31)];
     }
 }
 

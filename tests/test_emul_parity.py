@@ -166,3 +166,13 @@ def test_natural_order_in_place_fallback():
 def test_golden_vectors(napa):
     """shipped csrc (emulated) against the committed oracle fixtures"""
     S.check_golden(napa)
+
+
+@pytest.mark.parametrize("n,batch", [(2, 7), (16, 301), (256, 13), (1024, 5)])
+def test_bit_reverse_batches(napa, n, batch):
+    """several small vectors per CTA (ragged last CTA), complex and real"""
+    x = np.stack([S.rand_c(i, n) for i in range(min(batch, 64))] * ((batch + 63) // 64))[:batch]
+    p = S.revperm(n)
+    assert np.array_equal(napa.bit_reverse_batch(x.copy()), x[:, p])
+    xr = np.ascontiguousarray(x.real)
+    assert np.array_equal(napa.bit_reverse_batch(xr.copy()), xr[:, p])

@@ -243,3 +243,13 @@ def test_host_batches_across_staging_chunks(napa, lg, monkeypatch):
             assert S.nre(got[i], O.fft(x[i])) <= S.tol(n), (lg, rep, i)
         back = napa.fft_batch(got, direction=-1, scale=True)
         assert S.nre(back, x) <= S.tol(n), (lg, rep)
+
+
+@pytest.mark.parametrize("n,batch", [(2, 7), (16, 3001), (256, 1300), (1024, 517), (4096, 33)])
+def test_bit_reverse_batches(napa, n, batch):
+    """several small vectors per CTA (ragged last CTA), complex and real"""
+    x = np.stack([S.rand_c(i, n) for i in range(min(batch, 64))] * ((batch + 63) // 64))[:batch]
+    p = S.revperm(n)
+    assert np.array_equal(napa.bit_reverse_batch(x.copy()), x[:, p])
+    xr = np.ascontiguousarray(x.real)
+    assert np.array_equal(napa.bit_reverse_batch(xr.copy()), xr[:, p])
