@@ -580,6 +580,32 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             mbar_wait(mbar, mbar_parity);
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = LM == MAP_Q ? sm[(lpos(m) << LC) + q] : sm[(q << LOG2L) + lpos(m)];
+        } else if (flags & PF_RIFFT_PRE) {
+            // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177).  Two rounds of
+            // eight elements: a and b of a round are all in flight together (16 loads), the twiddles
+            // (L1/L2 hits) follow in fours -- two exposed DRAM latencies per tile and 112 live
+            // registers at most, instead of one latency per element or two.
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                cplx y[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const long long pos = (long long)lpos(8 * half + j) * s_i;
+                    v[8 * half + j] = ld_data<COHERENT>(src + pos, src_hint, pol);
+                    y[j] = ld_data<COHERENT>(src + pos + p.aux_off, src_hint, pol);
+                }
+#pragma unroll
+                for (int g4 = 0; g4 < 2; g4++) {
+                    cplx w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) w[j] = ldg_c(p.r2tw + s_xoff + (long long)lpos(8 * half + 4 * g4 + j) * s_i);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int m = 8 * half + 4 * g4 + j;
+                        v[m] = cadd(cadd(v[m], y[4 * g4 + j]), cmul(csub(v[m], y[4 * g4 + j]), w[j]));
+                    }
+                }
+            }
         } else if ((flags & PF_IN_REV) && !in_reorder) {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i, src_hint, pol);
@@ -588,26 +614,6 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             const long long step = (long long)T * s_i;
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(s0 + m * step, src_hint, pol);
-        }
-        if (flags & PF_RIFFT_PRE) {
-            // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177)
-            // partner and twiddle loads in batches of four (a 512-thread tile has no registers for more):
-            // four exposed latencies instead of one per element
-#pragma unroll
-            for (int g4 = 0; g4 < 4; g4++) {
-                cplx y[4], w[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const long long off = s_xoff + (long long)lpos(4 * g4 + j) * s_i;
-                    y[j] = ld_data<COHERENT>(src - s_xoff + off + p.aux_off, src_hint, pol);
-                    w[j] = ldg_c(p.r2tw + off);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int m = 4 * g4 + j;
-                    v[m] = cadd(cadd(v[m], y[j]), cmul(csub(v[m], y[j]), w[j]));
-                }
-            }
         }
         if (flags & PF_SCALE) {
             const double sc = p.scale;
