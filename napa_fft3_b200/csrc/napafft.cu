@@ -439,6 +439,7 @@ struct C2COpts {
     const void *window; int wtype; int wpb;
     bool rifft_pre = false; const cplx *r2tw = nullptr;
     bool rfft_post = false;    // single-pass only: fuse the rfft epilogue into the store (dst stride = 2n)
+    const double *zip_im = nullptr;   // single-pass only (%2rfft): src is a REAL vector, zip_im the second one; split epilogue in the store
 };
 
 // geometry of digit pass s (0-based) of an item with digits d[0..p)
@@ -526,6 +527,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         if (!inv && !o.in_order) pp.flags |= napa::PF_OUT_REV;
         first_pass_fusions(pp, o, n, win_rev);
         if (o.rfft_post) { pp.flags |= napa::PF_RFFT_POST; pp.r2tw = o.r2tw; }
+        if (o.zip_im) { pp.flags |= napa::PF_ZIP2 | napa::PF_SPLIT2_POST; pp.src_im = o.zip_im; }
         const long long C = 1LL << napa::plan_log2c(lg);
         OK(launch_pass(lg, KIND_ROW, pp, ((long long)batch + C - 1) / C, st));
         CU(cudaGetLastError());
@@ -612,7 +614,8 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         for (size_t b0 = 0; b0 < batch; b0 += chunk) {
             const size_t nb = std::min(chunk, batch - b0);
             long long tpi;
-            const cplx *cur = src + b0 * sstride;
+            // %2rfft: src is a vector of doubles (strides in doubles), zipped with o.zip_im on the first load
+            const cplx *cur = o.zip_im ? (const cplx *)((const double *)src + b0 * sstride) : src + b0 * sstride;
             long long cur_stride = (long long)sstride;
             for (int s = 0; s + 1 < p; s++) {
                 int lgB = 0;
@@ -626,6 +629,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                 p1.flags = napa::PF_TW_STORE | ((inv && s == 0) ? napa::PF_CONJ_IN : 0);
                 p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << (d[s] + lgB)) - 1;
                 if (s == 0) {
+                    if (o.zip_im) { p1.flags |= napa::PF_ZIP2; p1.src_im = o.zip_im + b0 * sstride; }
                     first_pass_fusions(p1, o, n, win_rev);
                     if (o.wpb && o.wtype) p1.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
                 }
@@ -863,6 +867,25 @@ static int exec_rifft(const cplx *src, double *dst, size_t n, size_t batch, int 
 }
 
 static int exec_2rfft(const double *v1, const double *v2, cplx *dst, size_t n, size_t batch, int scale, cudaStream_t st) {
+    const int lgn = ilog2(n);
+    if (lgn >= 7 && lgn <= 13 && !getenv("NAPAFFT_RFFT_UNFUSED")) {
+        // one launch: the two real vectors are zipped on load and the two spectra separated in the store
+        C2COpts z{};
+        z.dir = NAPA_FWD; z.in_order = 1; z.scale = scale_factor(n, NAPA_FWD, scale); z.zip_im = v2;
+        return exec_c2c((const cplx *)v1, dst, n, batch, n, 2 * n, z, st);
+    }
+    if (lgn >= 14 && !getenv("NAPAFFT_RFFT_UNFUSED")) {
+        // multi-pass sizes: the zip is fused into the first pass's load, the split stays a separate launch
+        C2COpts z{};
+        z.dir = NAPA_FWD; z.in_order = 1; z.scale = scale_factor(n, NAPA_FWD, scale); z.zip_im = v2;
+        OK(exec_c2c((const cplx *)v1, dst, n, batch, n, 2 * n, z, st));
+        const long long per2 = (long long)(n / 2) + 1, tot3 = per2 * (long long)batch;
+        NAPA_LAUNCH(napa::split2_post_kernel, (unsigned)((tot3 + 255) / 256), 256, 0, st, dst, (long long)(2 * n), (long long)batch,
+                    (long long)n);
+        g_launches++;
+        CU(cudaGetLastError());
+        return NAPA_OK;
+    }
     const long long total = (long long)n * (long long)batch;
     NAPA_LAUNCH(napa::zip2_kernel, (unsigned)((total + 255) / 256), 256, 0, st, v1, v2, dst, (long long)n, (long long)batch,
                 (long long)n, (long long)(2 * n));

@@ -162,6 +162,8 @@ enum : unsigned {
     PF_SCALE      = 1u << 10,
     PF_RIFFT_PRE  = 1u << 11,  // x = (a+b) + (a-b)*r2tw[off], b = src[off + N]   (real.lisp:170-177)
     PF_RFFT_POST  = 1u << 12,  // single-pass row tiles: rfft epilogue (real.lisp:16-30, 128-134) fused into the store
+    PF_ZIP2       = 1u << 13,  // %2rfft: the input is two REAL vectors, z = src[.] + i src_im[.] (strides in doubles)
+    PF_SPLIT2_POST = 1u << 14, // %2rfft: single-pass row tiles store the two spectra E (at i) and O (at L + i), real.lisp:16-30
 };
 
 struct PassParams {
@@ -190,6 +192,7 @@ struct PassParams {
     int tw_col_shift;
     const cplx *r2tw;                               // reference recurrence table (rifft pre-pass)
     long long aux_off;                              // N for PF_RIFFT_PRE
+    const double *src_im;                           // PF_ZIP2: the second real input
 };
 
 __device__ __forceinline__ cplx ldg_c(const cplx *p) { return __ldg(p); }
@@ -580,6 +583,14 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             mbar_wait(mbar, mbar_parity);
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = LM == MAP_Q ? sm[(lpos(m) << LC) + q] : sm[(q << LOG2L) + lpos(m)];
+        } else if (flags & PF_ZIP2) {
+            // %2rfft (real.lisp:33-48): two real vectors transformed as one complex vector
+            const long long base = (c.item + src_item_delta) * p.src_batch_stride + s_xoff;
+            const double *re = reinterpret_cast<const double *>(p.src) + base, *im = p.src_im + base;
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m].x = re[(long long)lpos(m) * s_i];
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m].y = im[(long long)lpos(m) * s_i];
         } else if (flags & PF_RIFFT_PRE) {
             // x = (a + b) + (a - b) * tw[off], b = src[off + N]   (real.lisp:170-177).  Two rounds of
             // eight elements: a and b of a round are all in flight together (16 loads), the twiddles
@@ -688,6 +699,32 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         }
     }
     if constexpr (LOG2L >= 7 && SM_ == MAP_T) {
+        if (flags & PF_SPLIT2_POST) {
+            // Z = FFT(v1 + i v2): E_i = FFT(v1)_i -> dst[i], O_i = FFT(v2)_i -> dst[L + i]; the same
+            // operations as split2_post_kernel, each thread finishing its own bins
+            Sync::sync();
+#pragma unroll
+            for (int m = 0; m < 16; m++) sm[(d.q << LOG2L) + d.t + m * T] = v[m];
+            Sync::sync();
+            if (d.valid) {
+                cplx *dst = p.dst + (d.item + dst_item_delta) * p.dst_batch_stride + d.d_xoff;
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const int i = d.t + m * T;
+                    const cplx x = v[m];
+                    if (i == 0) {
+                        st_data(dst, make_double2(x.x, 0.0), dst_hint, pol);
+                        st_data(dst + L, make_double2(x.y, 0.0), dst_hint, pol);
+                    } else {
+                        const cplx y = sm[(d.q << LOG2L) + (L - i)];
+                        const cplx oi = make_double2(0.5 * (x.y + y.y), 0.5 * (y.x - x.x));
+                        st_data(dst + i, make_double2(x.x + oi.y, x.y - oi.x), dst_hint, pol);
+                        st_data(dst + L + i, oi, dst_hint, pol);
+                    }
+                }
+            }
+            return;
+        }
         if (flags & PF_RFFT_POST) {
             // Z = FFT_L(packed reals) is complete inside the tile (q = one transform).  Each thread
             // finishes its own bins i: X[i] = E_i + O_i w^i, X[i + L] = E_i - O_i w^i with
