@@ -198,9 +198,8 @@ class ClockSampler:
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def main():
-    # keep stdout to the one JSON line: NCCL's version banner goes to stdout at NCCL_DEBUG=VERSION
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to the one JSON line: NCCL writes its version banner / warnings to stdout unless told otherwise
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
