@@ -117,7 +117,7 @@ template <> struct Radix<16> {
 // ------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int plan_nstages(int l) { return l <= 4 ? 1 : l <= 8 ? 2 : l <= 12 ? 3 : 4; }
 __host__ __device__ constexpr int plan_log2radix(int l, int s) {
-    // l: 4 [16] 5 [8,4] 6 [8,8] 7 [16,8] 8 [16,16] 9 [8,8,8] 10 [16,16,4] 11 [16,16,8]
+    // l: 4 [16] 5 [8,4] 6 [8,8] 7 [16,8] 8 [16,16] 9 [16,16,2] 10 [16,16,4] 11 [16,16,8]
     //    12 [16,16,16] 13 [16,16,8,4]
     switch (l) {
     case 4: return 4;
@@ -125,7 +125,7 @@ __host__ __device__ constexpr int plan_log2radix(int l, int s) {
     case 6: return 3;
     case 7: return s == 0 ? 4 : 3;
     case 8: return 4;
-    case 9: return 3;
+    case 9: return s < 2 ? 4 : 1;
     case 10: return s < 2 ? 4 : 2;
     case 11: return s < 2 ? 4 : 3;
     case 12: return 4;
