@@ -402,19 +402,19 @@ static std::vector<int> digits_of(int lg, bool natural = false) {
         }
         if (ok && sum == lg && v.size() >= 2 && v.size() <= 3) return v;
     }
-    // Measured on B200 with tools/sweep_digits.py (profiles/r01_sweep_digits.txt).  Column digits first.
+    // Measured on B200 with tools/sweep_digits.py (profiles/r01_sweep_digits.txt, r01_sweep_digits2.txt).  Column digits first.
     // Two passes while both sides keep >= 64..128-byte contiguous segments; the natural-order row pass
     // stores C*16-byte transposed segments (C = rows per tile), so it leaves the two-digit plans
     // sooner than the bit-reversed layouts, whose last pass is fully contiguous.  Three-digit plans
     // run every pass at copy speed (~1/3 of the roofline); larger digits go last.
-    // The plans of both output orders coincide up to 2^18 and from 2^23.
+    // The plans of both output orders coincide up to 2^16, at 2^18 and from 2^23.
     switch (lg) {
     case 14: return { 6, 8 };
     case 15: return { 7, 8 };
     case 16: return { 8, 8 };
-    case 17: return { 8, 9 };
+    case 17: return natural ? std::vector<int>{ 8, 9 } : std::vector<int>{ 9, 8 };
     case 18: return { 8, 10 };
-    case 19: return natural ? std::vector<int>{ 9, 10 } : std::vector<int>{ 8, 11 };
+    case 19: return natural ? std::vector<int>{ 9, 10 } : std::vector<int>{ 7, 12 };
     case 20: return natural ? std::vector<int>{ 9, 11 } : std::vector<int>{ 8, 12 };
     case 21: return natural ? std::vector<int>{ 6, 7, 8 } : std::vector<int>{ 9, 12 };
     case 22: return natural ? std::vector<int>{ 7, 7, 8 } : std::vector<int>{ 10, 12 };
