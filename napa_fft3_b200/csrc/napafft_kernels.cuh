@@ -117,15 +117,20 @@ template <> struct Radix<16> {
 // ------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int plan_nstages(int l) { return l <= 4 ? 1 : l <= 8 ? 2 : l <= 12 ? 3 : 4; }
 __host__ __device__ constexpr int plan_log2radix(int l, int s) {
-    // l: 4 [16] 5 [16,2] 6 [16,4] 7 [16,8] 8 [16,16] 9 [16,16,2] 10 [16,16,4] 11 [16,16,8]
-    //    12 [16,16,16] 13 [16,16,8,4] (16*16*16*2 measured equal)
+    // l: 4 [16] 5 [8,4] 6 [8,8] 7 [16,8] 8 [16,16] 9 [16,16,2] 10 [16,16,4] 11 [16,16,8]
+    //    12 [16,16,16] 13 [16,16,8,4]   (interleaved A/B on one box, tools/ab_plans.py: 16*16*2 beats 8*8*8 by 3 % at
+    //    L = 512; 16*2 / 16*4 lose 1-3 % to 8*4 / 8*8 at L = 32 / 64; 16*16*16*2 equals 16*16*8*4 at L = 8192)
     switch (l) {
     case 4: return 4;
-    case 5: return s == 0 ? 4 : 1;
-    case 6: return s == 0 ? 4 : 2;
+    case 5: return s == 0 ? 3 : 2;
+    case 6: return 3;
+#ifdef NAPA_PLAN_OLD   /* A/B build of the earlier 8*8*8 plan (tools/ab_plans.py) */
+    case 9: return 3;
+#else
+    case 9: return s < 2 ? 4 : 1;
+#endif
     case 7: return s == 0 ? 4 : 3;
     case 8: return 4;
-    case 9: return s < 2 ? 4 : 1;
     case 10: return s < 2 ? 4 : 2;
     case 11: return s < 2 ? 4 : 3;
     case 12: return 4;

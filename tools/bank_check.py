@@ -6,7 +6,7 @@ it replays the 16-byte addresses of every warp instruction and counts 128-byte w
 Run: python tools/bank_check.py      (exits non-zero on any conflict)"""
 import sys
 
-PLANS = {4: [4], 5: [4, 1], 6: [4, 2], 7: [4, 3], 8: [4, 4], 9: [4, 4, 1], 10: [4, 4, 2], 11: [4, 4, 3],
+PLANS = {4: [4], 5: [3, 2], 6: [3, 3], 7: [4, 3], 8: [4, 4], 9: [4, 4, 1], 10: [4, 4, 2], 11: [4, 4, 3],
          12: [4, 4, 4], 13: [4, 4, 3, 2]}
 SMALL_TILE_MAXL = 8
 
