@@ -78,6 +78,7 @@ struct State {
     void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = (size_t)1 << 30; // items per launch of the multi-launch path (also the natural-order scratch size)
     std::map<cudaStream_t, std::pair<cplx *, size_t>> oa_buf;    // chunk matrix + energies of the overlap-add filter, one per stream
+    size_t zero_copy_bytes = 128 << 10;   // host-pointer jobs up to this size run on mapped page-locked memory, no copies
     size_t max_scratch_bytes = (size_t)16 << 30;   // natural-order scratch copy up to this size, else in-place fallback
     size_t pipe_l2_bytes = 40u << 20;     // live intermediate of the group-fused kernel (groups * n * 16 B)
     int pipe_gsize = 0;                   // CTAs per group (0 = auto)
@@ -1019,6 +1020,26 @@ static int run_host_job(const HostJob &j, Body body) {
     const size_t per_item = j.inplace ? std::max(in_total, j.out_item_bytes) : in_total + j.out_item_bytes;
     size_t target = (size_t)256 << 20;                                    // device bytes per chunk
     if (const char *e = getenv("NAPAFFT_STAGE_MB")) target = (size_t)atoll(e) << 20;
+    const size_t small_in = in_total * j.batch, small_out = j.out_item_bytes * j.batch;
+    if (small_in + small_out <= G.zero_copy_bytes) {
+        // Small job (a single 2^10 transform is 32 KiB): no copy launches at all.  The operands are packed into
+        // the page-locked ring, the kernels read and write that host memory directly over PCIe (unified
+        // addressing), one stream synchronisation, unpack.  Three driver calls instead of five.
+        OK(ensure_staging(0));
+        const size_t in_span = (small_in + 255) & ~(size_t)255;
+        OK(ensure_pinned(j.inplace ? std::max(in_span, small_out) : in_span + small_out));
+        char *hin = (char *)G.pinned[0], *hout = j.inplace ? hin : hin + in_span;
+        for (int which = 0; which < (j.src2 ? 2 : 1); which++) {
+            const char *hs = which ? j.src2 : j.src;
+            char *ph = hin + (which ? j.batch * j.in_item_bytes : 0);
+            for (size_t i = 0; i < j.batch; i++) memcpy(ph + i * j.in_item_bytes, hs + i * j.in_pitch, j.in_item_bytes);
+        }
+        cudaStream_t st = G.stream[0];
+        OK(body(hin, hout, j.batch, 0, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < j.batch; i++) memcpy(j.dst + i * j.out_pitch, hout + i * j.out_item_bytes, j.out_item_bytes);
+        return NAPA_OK;
+    }
     const size_t items = std::max<size_t>(1, std::min(j.batch, target / std::max<size_t>(per_item, 1)));
     OK(ensure_staging(items * per_item + 256));
     const bool src_pinned = is_pinned(j.src) && (!j.src2 || is_pinned(j.src2));
@@ -1094,6 +1115,7 @@ NAPA_API int napafft_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(NAPA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
+    if (const char *env = getenv("NAPAFFT_ZERO_COPY_KB")) G.zero_copy_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_MAX_SCRATCH_KB")) G.max_scratch_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_PIPE_L2_MB")) G.pipe_l2_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_PIPE_GSIZE")) G.pipe_gsize = atoi(env);
