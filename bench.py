@@ -227,6 +227,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL's version banner is written through C stdio when the communicator comes up: force that now and
+        # flush libc's buffer, so that the JSON line below is the last thing on stdout
+        dist.barrier()
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
