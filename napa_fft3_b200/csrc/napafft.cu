@@ -327,7 +327,9 @@ static void pipeline_shape(long long W, size_t n, size_t batch, long long T, nap
     if (G.pipe_gsize > 0) gs = std::min<long long>(std::min<long long>(G.pipe_gsize, T), W);
     ng = std::min<long long>(std::max<long long>(1, W / gs), (long long)batch);
 #ifdef NAPA_EMULATE
-    gs = 1; ng = std::min<long long>(3, (long long)batch);     // the emulator runs CTAs one after the other: no inter-CTA waits
+    // the emulator keeps every fiber of a cooperative grid alive: a small grid of real multi-CTA groups
+    gs = std::min<long long>(T, 4); ng = std::min<long long>(3, (long long)batch);
+    if (G.pipe_gsize > 0) gs = std::min<long long>(G.pipe_gsize, T);
 #endif
     pp.items = (long long)batch; pp.gsize = (int)gs; pp.ngroups = (int)ng;
     pp.tiles_a = pp.tiles_b = (int)T;
@@ -377,7 +379,7 @@ static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStr
     }
 #endif
 #ifdef NAPA_EMULATE
-    NAPA_LAUNCH(fn, grid, napa::plan_threads(la), smem, st, pp);
+    NAPA_LAUNCH_COOP(fn, grid, napa::plan_threads(la), smem, st, pp);
 #else
     // cooperative launch: every CTA of the grid is resident before any of them waits on another
     void *args[] = { (void *)&pp };

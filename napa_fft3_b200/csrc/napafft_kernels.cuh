@@ -211,7 +211,7 @@ __device__ __forceinline__ L2Policies make_policies() { return L2Policies{0}; }
 template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, int, const L2Policies &) { return *p; }
 __device__ __forceinline__ void st_data(cplx *p, cplx v, int, const L2Policies &) { *p = v; }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
-__device__ __forceinline__ void napa_nanosleep(unsigned) {}
+__device__ __forceinline__ void napa_nanosleep(unsigned) { napa_emul::yield_spin(); }   // let the other CTAs' fibers run
 // bulk-copy staging: the emulator copies synchronously and never waits
 __device__ __forceinline__ void mbar_init(unsigned long long *, unsigned) {}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *, unsigned) {}

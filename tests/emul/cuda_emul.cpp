@@ -49,9 +49,10 @@ void bar_sync(int id, unsigned count) {
     while (bar_gen[id] == g) yield_fiber();
 }
 
-void syncthreads() { bar_sync(0, blockDim_.x * blockDim_.y * blockDim_.z); }
+void syncthreads();
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    // (plain launches: CTAs one after the other, see launch_cooperative below for the all-alive mode)
     const unsigned nthreads = block.x * block.y * block.z;
     if (fibers.size() < nthreads) {
         size_t old = fibers.size();
@@ -94,6 +95,93 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
         }
     }
     free(sm);
+    dyn_smem = nullptr;
+    cur_body = nullptr;
+}
+
+
+// ---- cooperative launch: every CTA of the grid is alive at once (group barriers between CTAs) ----
+// One fiber per thread of the WHOLE grid, scheduled round-robin; __syncthreads() is per CTA, the
+// dynamic shared memory is per CTA and swapped in with the fiber, and a fiber that spins on another
+// CTA's progress gives way through yield_spin().
+namespace {
+struct CoopBlock { unsigned arrived; unsigned long long gen; unsigned char *smem; };
+std::vector<CoopBlock> coop_blocks;
+std::vector<Fiber> coop_fibers;
+bool coop_mode = false;
+unsigned coop_threads = 0;
+int coop_current = -1;
+void coop_trampoline() {
+    (*cur_body)();
+    coop_fibers[coop_current].st = DONE;
+    swapcontext(&coop_fibers[coop_current].ctx, &sched_ctx);
+}
+void coop_yield() {
+    coop_fibers[coop_current].st = AT_BARRIER;
+    swapcontext(&coop_fibers[coop_current].ctx, &sched_ctx);
+}
+}  // namespace
+
+void yield_spin() {
+    if (coop_mode) coop_yield();
+}
+
+void syncthreads() {
+    if (!coop_mode) { bar_sync(0, blockDim_.x * blockDim_.y * blockDim_.z); return; }
+    CoopBlock &cb = coop_blocks[(size_t)coop_current / coop_threads];
+    progress++;
+    if (++cb.arrived >= coop_threads) { cb.arrived = 0; cb.gen++; return; }
+    const unsigned long long g = cb.gen;
+    while (cb.gen == g) coop_yield();
+}
+
+void launch_cooperative(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    const unsigned nthreads = block.x * block.y * block.z, nblocks = grid.x * grid.y * grid.z;
+    const size_t total = (size_t)nthreads * nblocks;
+    if (coop_fibers.size() < total) {
+        size_t old = coop_fibers.size();
+        coop_fibers.resize(total);
+        for (size_t i = old; i < total; i++) coop_fibers[i].stack = (unsigned char *)malloc(kStack);
+    }
+    coop_blocks.assign(nblocks, CoopBlock{0, 0, nullptr});
+    for (unsigned b = 0; b < nblocks; b++) {
+        void *sm = nullptr;
+        if (posix_memalign(&sm, 128, smem ? smem : 16)) abort();
+        coop_blocks[b].smem = (unsigned char *)sm;
+    }
+    blockDim_ = block; gridDim_ = grid;
+    cur_body = &body;
+    coop_mode = true; coop_threads = nthreads;
+    for (size_t i = 0; i < total; i++) {
+        Fiber &f = coop_fibers[i];
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = kStack;
+        f.ctx.uc_link = &sched_ctx;
+        makecontext(&f.ctx, coop_trampoline, 0);
+        f.st = READY;
+    }
+    for (;;) {
+        size_t live = 0;
+        const unsigned long long before = progress;
+        for (size_t i = 0; i < total; i++) {
+            Fiber &f = coop_fibers[i];
+            if (f.st == DONE) continue;
+            const unsigned b = (unsigned)(i / nthreads), t = (unsigned)(i % nthreads);
+            coop_current = (int)i;
+            blockIdx_ = { b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y) };
+            threadIdx_ = { t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
+            dyn_smem = coop_blocks[b].smem;
+            f.st = READY;
+            swapcontext(&sched_ctx, &f.ctx);
+            if (f.st != DONE) live++; else progress++;
+        }
+        if (live == 0) break;
+        if (progress == before) { fprintf(stderr, "napa_emul: cooperative launch made no progress (deadlock)\n"); abort(); }
+    }
+    for (unsigned b = 0; b < nblocks; b++) free(coop_blocks[b].smem);
+    coop_blocks.clear();
+    coop_mode = false;
     dyn_smem = nullptr;
     cur_body = nullptr;
 }

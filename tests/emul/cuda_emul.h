@@ -5,7 +5,8 @@
 // by the product package: the product library is nvcc-compiled sm_100a code with no CPU path.
 //
 // Threads of a CTA are ucontext fibers run round-robin on one OS thread; __syncthreads() yields to
-// the scheduler until every live fiber of the CTA has arrived.  CTAs run one after another.
+// the scheduler until every live fiber of the CTA has arrived.  CTAs run one after another, except in
+// launch_cooperative(), which keeps the fibers of the whole grid alive so that CTAs can wait on each other.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -38,6 +39,9 @@ extern uint3_ threadIdx_, blockIdx_;
 extern dim3 blockDim_, gridDim_;
 extern unsigned char *dyn_smem;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
+// every CTA alive at once (round-robin over all fibers of the grid): kernels whose CTAs wait on each other
+void launch_cooperative(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
+void yield_spin();                           // called from a spin-wait on another CTA's progress
 void syncthreads();
 void bar_sync(int id, unsigned count);      // named barrier (bar.sync id, count)
 void bar_arrive(int id, unsigned count);    // bar.arrive id, count
@@ -64,6 +68,8 @@ static inline unsigned long long __brevll(unsigned long long x) {
 #define NAPA_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(napa_emul::dyn_smem)
 #define NAPA_LAUNCH(kern, grid, block, smem, stream, ...) \
     napa_emul::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })
+#define NAPA_LAUNCH_COOP(kern, grid, block, smem, stream, ...) \
+    napa_emul::launch_cooperative(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })
 
 // ---- minimal runtime -------------------------------------------------------------------
 typedef int cudaError_t;

@@ -118,15 +118,16 @@ def test_many_tiles_single_pass(napa, n, batch):
 
 
 def test_optional_l2_pipeline_path():
-    """the group-fused two-pass kernel (off by default, NAPAFFT_PIPELINE=1) stays correct:
-    scratch-slot reuse across a group's transforms, staged tiles, natural and bit-reversed plans (the emulator
-    runs CTAs one after the other, so groups are one CTA wide here; the group barrier itself is exercised by
-    tests/test_gpu_parity.py on a B200)"""
+    """the group-fused two-pass kernel (off by default, NAPAFFT_PIPELINE=1) stays correct: real multi-CTA groups
+    (the emulator keeps every CTA of a cooperative launch alive, tests/emul/cuda_emul.cpp: launch_cooperative),
+    group barriers, scratch-slot reuse across a group's transforms, staged tiles, natural and bit-reversed plans;
+    groups of 4 CTAs (several tiles per CTA and phase) and of 8 (one tile per CTA and phase at 2^14)"""
     import subprocess
-    env = dict(os.environ, NAPAFFT_PIPELINE="1")
-    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
-                         env=env, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    for extra in ({}, {"NAPAFFT_PIPE_GSIZE": "8"}):
+        env = dict(os.environ, NAPAFFT_PIPELINE="1", **extra)
+        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
+                             env=env, capture_output=True, text=True, timeout=1200)
+        assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("digits,n", [("5,5,6", 1 << 16), ("7,8", 1 << 15), ("6,5,6", 1 << 17)])
