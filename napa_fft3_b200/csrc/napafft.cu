@@ -80,9 +80,9 @@ struct State {
     std::map<cudaStream_t, std::pair<cplx *, size_t>> oa_buf;    // chunk matrix + energies of the overlap-add filter, one per stream
     size_t zero_copy_bytes = 128 << 10;   // host-pointer jobs up to this size run on mapped page-locked memory, no copies
     size_t max_scratch_bytes = (size_t)16 << 30;   // natural-order scratch copy up to this size, else in-place fallback
-    size_t pipe_l2_bytes = 40u << 20;     // live intermediate of the group-fused kernel (groups * n * 16 B)
-    int pipe_gsize = 0;                   // CTAs per group (0 = auto)
-    bool use_pipeline = false;            // group-fused two-pass kernel: ties with two plain launches today
+    size_t fused_unit_bytes = 20u << 20;  // fused kernel: largest unit of intermediate (two units are live in L2)
+    int fused_upg = 0, fused_grid = 0;    // tuning overrides: transforms per unit, CTAs (0 = auto)
+    bool use_fused = true;                // fused single-launch plans for 2^14 .. 2^20 (NAPAFFT_FUSED=0: one launch per digit pass)
     bool attrs_set = false;
     int num_sms = 148;
     std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream group-barrier counters
@@ -260,22 +260,23 @@ static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStr
     return NAPA_OK;
 }
 
-// group-fused two-pass kernels: (first-executed digit, second digit, plan kind)
-typedef void (*pipe_fn)(const napa::PipeParams);
-#ifndef NAPA_EMULATE
-typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-#endif
-#define NAPA_PIPE_CASE(a, b)                                                    \
-    if (la == a && lb == b)                                                     \
-        return pk == 0 ? napa::fft_pipeline_kernel<a, b, 0> : (pk == 1 ? napa::fft_pipeline_kernel<a, b, 1> : napa::fft_pipeline_kernel<a, b, 2>);
-static pipe_fn pipe_kernel(int la, int lb, int pk) {
-    NAPA_PIPE_CASE(7, 7) NAPA_PIPE_CASE(7, 8) NAPA_PIPE_CASE(8, 7) NAPA_PIPE_CASE(8, 8)
-    NAPA_PIPE_CASE(9, 9) NAPA_PIPE_CASE(9, 10)
-    NAPA_PIPE_CASE(10, 9) NAPA_PIPE_CASE(10, 10) NAPA_PIPE_CASE(10, 11) NAPA_PIPE_CASE(11, 10)
-    NAPA_PIPE_CASE(10, 12) NAPA_PIPE_CASE(12, 10)
+// fused two-pass kernels: (first-executed digit, second digit, plan kind, window fusions compiled in)
+typedef void (*fused_fn)(const napa::FusedParams);
+#define NAPA_FUSED_CASE(a, b)                                                                     \
+    if (la == a && lb == b) {                                                                     \
+        if (win) return pk == 0 ? napa::fft_fused_kernel<a, b, 0, true> : (pk == 1 ? napa::fft_fused_kernel<a, b, 1, true> : napa::fft_fused_kernel<a, b, 2, true>); \
+        return pk == 0 ? napa::fft_fused_kernel<a, b, 0, false> : (pk == 1 ? napa::fft_fused_kernel<a, b, 1, false> : napa::fft_fused_kernel<a, b, 2, false>); \
+    }
+static fused_fn fused_kernel(int la, int lb, int pk, bool win) {
+    NAPA_FUSED_CASE(7, 7) NAPA_FUSED_CASE(7, 8) NAPA_FUSED_CASE(8, 7) NAPA_FUSED_CASE(8, 8)
+    NAPA_FUSED_CASE(9, 9) NAPA_FUSED_CASE(9, 10) NAPA_FUSED_CASE(10, 9) NAPA_FUSED_CASE(10, 10)
     return nullptr;
+}
+// column digit of the fused plan for 2^lg (0 = no fused kernel: the digits would need two tile shapes,
+// or two units of intermediate would not fit in L2)
+static int fused_col_digit(int lg) {
+    static const int l1[] = { 7, 7, 8, 0, 9, 9, 10 };      // lg = 14 .. 20
+    return lg >= 14 && lg <= 20 ? l1[lg - 14] : 0;
 }
 
 static int ensure_counters(cudaStream_t st, size_t bytes, unsigned char **out) {
@@ -299,91 +300,81 @@ static int ensure_counters(cudaStream_t st, size_t bytes, unsigned char **out) {
     return NAPA_OK;
 }
 
-// resident CTAs of a pipeline kernel (cached)
-static int pipeline_resident(int la, int lb, int pk, long long *out) {
-    pipe_fn fn = pipe_kernel(la, lb, pk);
-    if (!fn) return fail(NAPA_E_UNSUPPORTED, "no pipeline kernel for digits (%d, %d)", la, lb);
-    static std::map<pipe_fn, int> occ;
+// A wait inside the fused kernel that timed out leaves its flag set (never expected: it means a CTA of a
+// cooperative launch was lost).  Checked at the start of every later call and by napafft_sync paths.
+static int check_device_error() {
+    if (G.h_error && *G.h_error) {
+        *G.h_error = 0;
+        return fail(NAPA_E_CUDA, "a fused-kernel dependency wait timed out; results of the previous launch are invalid");
+    }
+    return NAPA_OK;
+}
+
+// resident CTAs of a fused kernel (cached)
+static int fused_resident(fused_fn fn, int threads, size_t smem, long long *out) {
+    static std::map<fused_fn, int> occ;
     auto it = occ.find(fn);
     if (it == occ.end()) {
-        const size_t smem = napa::pipe_smem_bytes(la, lb, pk);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, napa::plan_threads(la), smem));
-        if (nb < 1) return fail(NAPA_E_CUDA, "pipeline kernel does not fit on an SM");
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, threads, smem));
+        if (nb < 1) return fail(NAPA_E_CUDA, "fused kernel does not fit on an SM");
         it = occ.emplace(fn, nb).first;
     }
     *out = (long long)G.num_sms * it->second;
     return NAPA_OK;
 }
 
-// Shape of the group-fused launch.  W = co-resident CTAs, T = tiles per transform and pass.  The
-// live intermediate is ngroups * n * 16 bytes: ngroups is capped so that it stays within
-// G.pipe_l2_bytes (a fraction of the 126 MB L2), and a group is never wider than T CTAs.
-static void pipeline_shape(long long W, size_t n, size_t batch, long long T, napa::PipeParams &pp) {
-    long long ng = std::max<long long>(1, (long long)(G.pipe_l2_bytes / (n * sizeof(cplx))));
-    ng = std::min<long long>(ng, (long long)batch);
-    long long gs = std::min<long long>(T, std::max<long long>(1, W / ng));
-    if (G.pipe_gsize > 0) gs = std::min<long long>(std::min<long long>(G.pipe_gsize, T), W);
-    ng = std::min<long long>(std::max<long long>(1, W / gs), (long long)batch);
-#ifdef NAPA_EMULATE
-    // the emulator keeps every fiber of a cooperative grid alive: a small grid of real multi-CTA groups
-    gs = std::min<long long>(T, 4); ng = std::min<long long>(3, (long long)batch);
-    if (G.pipe_gsize > 0) gs = std::min<long long>(G.pipe_gsize, T);
-#endif
-    pp.items = (long long)batch; pp.gsize = (int)gs; pp.ngroups = (int)ng;
-    pp.tiles_a = pp.tiles_b = (int)T;
-}
-
-static int launch_pipeline(int la, int lb, int pk, napa::PipeParams &pp, cudaStream_t st) {
-    pipe_fn fn = pipe_kernel(la, lb, pk);
+// One cooperative launch over the whole batch.  The grid is every co-resident CTA; a unit is about one tile
+// per CTA and pass, capped so that two units of intermediate stay well inside L2 (G.fused_unit_bytes).
+static int launch_fused(int la, int lb, int pk, bool win, size_t n, size_t batch, napa::FusedParams &fp, bool ring,
+                        cudaStream_t st) {
+    fused_fn fn = fused_kernel(la, lb, pk, win);
     if (!fn) return fail(NAPA_E_UNSUPPORTED, "no fused kernel for digits (%d, %d)", la, lb);
+    OK(check_device_error());
     OK(ensure_stage_tw(la));
     OK(ensure_stage_tw(lb));
-    pp.a.stage_tw = G.stage_tw[la];
-    pp.b.stage_tw = G.stage_tw[lb];
-    pp.a.lg_tpi = ilog2((size_t)pp.a.tiles_per_item); pp.a.lg_G = ilog2((size_t)pp.a.G);
-    pp.b.lg_tpi = ilog2((size_t)pp.b.tiles_per_item); pp.b.lg_G = ilog2((size_t)pp.b.G);
-    const size_t smem = napa::pipe_smem_bytes(la, lb, pk);
-    const size_t cbytes = (size_t)pp.ngroups * 32 * sizeof(unsigned);
+    fp.a.stage_tw = G.stage_tw[la];
+    fp.b.stage_tw = G.stage_tw[lb];
+    fp.a.lg_tpi = ilog2((size_t)fp.a.tiles_per_item); fp.a.lg_G = ilog2((size_t)fp.a.G);
+    fp.b.lg_tpi = ilog2((size_t)fp.b.tiles_per_item); fp.b.lg_G = ilog2((size_t)fp.b.G);
+    const size_t smem = napa::fused_smem_bytes(la, lb, pk);
+    const int threads = napa::plan_threads(la);
+    long long W;
+    OK(fused_resident(fn, threads, smem, &W));
+    if (G.fused_grid > 0) W = std::min<long long>(W, G.fused_grid);
+    const long long tpi = (long long)(n >> napa::plan_log2pts(la));
+    long long upg = std::max<long long>(1, (W + tpi - 1) / tpi);
+    upg = std::min<long long>(upg, std::max<long long>(1, (long long)(G.fused_unit_bytes / (n * sizeof(cplx)))));
+    if (G.fused_upg > 0) upg = G.fused_upg;
+    upg = std::min<long long>(upg, (long long)batch);
+#ifdef NAPA_EMULATE
+    // the emulator keeps every fiber of a cooperative grid alive: a small grid, several tiles per CTA and phase
+    W = std::min<long long>(W, 3);
+    if (G.fused_upg <= 0) upg = std::min<long long>(2, (long long)batch);
+#endif
+    const long long nunits = ((long long)batch + upg - 1) / upg;
+    if (nunits > 0x3fffffffLL) return fail(NAPA_E_UNSUPPORTED, "batch too large for one fused launch");
+    fp.items = (long long)batch; fp.upg = (int)upg; fp.nunits = (int)nunits;
+    if (ring) {
+        // natural order: the intermediate of units u and u + 1 (ring slots u & 1)
+        cplx *buf;
+        OK(ensure_scratch(st, (size_t)(2 * upg) * n * sizeof(cplx), &buf));
+        fp.a.dst = buf; fp.b.src = buf;
+    }
+    const size_t cbytes = (size_t)nunits * 2 * sizeof(unsigned);
     unsigned char *ctr;
     OK(ensure_counters(st, cbytes, &ctr));
     CU(cudaMemsetAsync(ctr, 0, cbytes, st));
-    pp.bar = (unsigned *)ctr;
-    pp.error = G.d_error;
-    if (const char *env = getenv("NAPAFFT_DEBUG")) pp.debug = atoi(env);
-    if (pp.debug & 2) { pp.a.src_hint = pp.a.dst_hint = pp.b.src_hint = pp.b.dst_hint = 0; }
-    const unsigned grid = (unsigned)(pp.gsize * pp.ngroups);
-#ifndef NAPA_EMULATE
-    if (napa::pipe_staged(la, lb)) {
-        // tensor map of the column pass's source (pass A, or pass B of the inverse bit-reversed plan):
-        // doubles [item][row][2 * col], one box = one tile = L rows x C columns
-        const PassParams &cp = pk == 2 ? pp.b : pp.a;
-        const int lc = pk == 2 ? lb : la;
-        static tmap_encode_fn enc = nullptr;
-        if (!enc) {
-            void *fp = nullptr; cudaDriverEntryPointQueryResult qr;
-            CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr));
-            if (!fp || qr != cudaDriverEntryPointSuccess) return fail(NAPA_E_CUDA, "cuTensorMapEncodeTiled is not available");
-            enc = (tmap_encode_fn)fp;
-        }
-        const cuuint64_t B = (cuuint64_t)cp.s_i, L = 1ull << lc, C = 1ull << napa::plan_log2c(lc);
-        const cuuint64_t gdim[3] = { 2 * B, L, (cuuint64_t)pp.items };
-        const cuuint64_t gstr[2] = { B * sizeof(cplx), (cuuint64_t)cp.src_batch_stride * sizeof(cplx) };
-        const cuuint32_t box[3] = { (cuuint32_t)(2 * C), (cuuint32_t)L, 1 };
-        const cuuint32_t estr[3] = { 1, 1, 1 };
-        CUresult cr = enc((CUtensorMap *)pp.col_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)cp.src, gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return fail(NAPA_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    }
-#endif
+    fp.done_a = (unsigned *)ctr; fp.done_b = fp.done_a + nunits;
+    fp.error = G.d_error;
+    const unsigned grid = (unsigned)std::min<long long>(W, std::max<long long>(1, upg * tpi));
 #ifdef NAPA_EMULATE
-    NAPA_LAUNCH_COOP(fn, grid, napa::plan_threads(la), smem, st, pp);
+    NAPA_LAUNCH_COOP(fn, grid, threads, smem, st, fp);
 #else
     // cooperative launch: every CTA of the grid is resident before any of them waits on another
-    void *args[] = { (void *)&pp };
-    CU(cudaLaunchCooperativeKernel((const void *)fn, dim3(grid), dim3(napa::plan_threads(la)), args, smem, st));
+    void *args[] = { (void *)&fp };
+    CU(cudaLaunchCooperativeKernel((const void *)fn, dim3(grid), dim3(threads), args, smem, st));
 #endif
     g_launches++;
     return NAPA_OK;
@@ -512,11 +503,6 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     }
 
     std::vector<int> d = digits_of(lg, o.in_order != 0);
-    if (G.use_pipeline && !getenv("NAPAFFT_DIGITS")) {
-        // the group-fused kernel is instantiated for digit pairs sharing one tile shape
-        static const int pipe_l1[] = { 7, 7, 8, 0, 9, 9, 10, 10, 10 };     // lg = 14 .. 22
-        if (lg >= 14 && lg <= 22 && pipe_l1[lg - 14]) d = { pipe_l1[lg - 14], lg - pipe_l1[lg - 14] };
-    }
     const int p = (int)d.size();
 
     if (p == 1) {
@@ -542,46 +528,40 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     chunk = std::min(chunk, batch);
 
     const bool natural = o.in_order != 0;
-    const bool can_pipe = G.use_pipeline && p == 2 && d[0] <= 12 && d[1] <= 12 &&
-                          napa::plan_log2pts(d[0]) == napa::plan_log2pts(d[1]);   // one tile shape per pipeline
-    if (can_pipe) {
-        napa::PipeParams pp{};
+    const int fcol = G.use_fused ? fused_col_digit(lg) : 0;
+    if (fcol && !getenv("NAPAFFT_DIGITS")) {
+        // one persistent launch for the whole batch, the intermediate stays in L2 (napafft_kernels.cuh: fft_fused_kernel)
+        const std::vector<int> fd = { fcol, lg - fcol };
+        napa::FusedParams fp{};
         const int pk = natural ? 0 : (inv ? 2 : 1);
-        const int la = pk == 2 ? d[1] : d[0], lb = pk == 2 ? d[0] : d[1];
-        long long W;
-        OK(pipeline_resident(la, lb, pk, &W));
-        pipeline_shape(W, n, batch, (long long)(n >> napa::plan_log2pts(d[0])), pp);
+        const bool win = o.wtype != 0 || o.zip_im || o.rifft_pre;
+        BigTw bt; OK(ensure_big_tw(lg, &bt));
         long long tpi;
         if (natural) {
-            // A: column pass src -> the group's scratch slot (+ inter-pass twiddle); B: row pass slot -> dst, transposed store
-            cplx *scratch; OK(ensure_scratch(st, (size_t)pp.ngroups * n * sizeof(cplx), &scratch));
-            BigTw bt; OK(ensure_big_tw(lg, &bt));
-            PassParams &p1 = pp.a, &p2 = pp.b;
-            pass_geometry(d, 0, p1, &tpi);
-            p1.src = src; p1.dst = scratch;
+            // A: column pass src -> ring slot (+ inter-pass twiddle); B: row pass slot -> dst, transposed store
+            PassParams &p1 = fp.a, &p2 = fp.b;
+            pass_geometry(fd, 0, p1, &tpi);
+            p1.src = src;
             p1.src_batch_stride = (long long)sstride; p1.dst_batch_stride = (long long)n; p1.batch = (long long)batch;
             p1.flags = napa::PF_TW_STORE | (inv ? napa::PF_CONJ_IN : 0);
             p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << lg) - 1;
+            if (o.zip_im) { p1.flags |= napa::PF_ZIP2; p1.src_im = o.zip_im; }
             first_pass_fusions(p1, o, n, win_rev);
-            pass_geometry(d, 1, p2, &tpi);
-            p2.src = scratch; p2.dst = dst;
+            pass_geometry(fd, 1, p2, &tpi);
+            p2.dst = dst;
             p2.src_batch_stride = (long long)n; p2.dst_batch_stride = (long long)dstride; p2.batch = (long long)batch;
             p2.flags = inv ? napa::PF_CONJ_OUT : 0;
-            p2.d_SA = 1LL << napa::plan_log2c(d[1]); p2.d_SG = 0; p2.d_i = 1LL << d[0]; p2.d_q = 1;
-            pp.a_dst_is_ring = 1; pp.b_src_is_ring = 1;
-            p1.src_hint = napa::HINT_STREAM; p1.dst_hint = napa::HINT_KEEP;
-            p2.src_hint = napa::HINT_KEEP; p2.dst_hint = napa::HINT_STREAM;
-            OK(launch_pipeline(d[0], d[1], 0, pp, st));
+            p2.d_SA = 1LL << napa::plan_log2c(fd[1]); p2.d_SG = 0; p2.d_i = 1LL << fd[0]; p2.d_q = 1;
+            OK(launch_fused(fd[0], fd[1], 0, win, n, batch, fp, true, st));
         } else {
             // bit-reversed layouts: in place on dst after the first pass, no scratch
             const int sa = inv ? 1 : 0, sb = inv ? 0 : 1;      // DIT runs the digits last to first
-            BigTw bt; OK(ensure_big_tw(lg, &bt));
-            PassParams *ps[2] = { &pp.a, &pp.b };
+            PassParams *ps[2] = { &fp.a, &fp.b };
             const int order[2] = { sa, sb };
             for (int step = 0; step < 2; step++) {
                 PassParams &q = *ps[step];
                 const int sdig = order[step];
-                pass_geometry(d, sdig, q, &tpi);
+                pass_geometry(fd, sdig, q, &tpi);
                 q.src = step == 0 ? src : dst; q.dst = dst;
                 q.src_batch_stride = (long long)(step == 0 ? sstride : dstride); q.dst_batch_stride = (long long)dstride;
                 q.batch = (long long)batch;
@@ -593,11 +573,8 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                 if (inv && step == 0) q.flags |= napa::PF_CONJ_IN;
                 if (inv && step == 1) q.flags |= napa::PF_CONJ_OUT;
                 if (step == 0) first_pass_fusions(q, o, n, false);
-                // in place: the intermediate lives in dst between the passes
-                q.src_hint = step == 0 ? napa::HINT_STREAM : napa::HINT_KEEP;
-                q.dst_hint = step == 0 ? napa::HINT_KEEP : napa::HINT_STREAM;
             }
-            OK(launch_pipeline(d[order[0]], d[order[1]], inv ? 2 : 1, pp, st));
+            OK(launch_fused(fd[order[0]], fd[order[1]], inv ? 2 : 1, win, n, batch, fp, false, st));
         }
         CU(cudaGetLastError());
         return NAPA_OK;
@@ -1119,9 +1096,10 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_ZERO_COPY_KB")) G.zero_copy_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_MAX_SCRATCH_KB")) G.max_scratch_bytes = (size_t)atoll(env) << 10;
-    if (const char *env = getenv("NAPAFFT_PIPE_L2_MB")) G.pipe_l2_bytes = (size_t)atoll(env) << 20;
-    if (const char *env = getenv("NAPAFFT_PIPE_GSIZE")) G.pipe_gsize = atoi(env);
-    if (const char *env = getenv("NAPAFFT_PIPELINE")) G.use_pipeline = atoi(env) != 0;
+    if (const char *env = getenv("NAPAFFT_FUSED_UNIT_MB")) G.fused_unit_bytes = (size_t)atoll(env) << 20;
+    if (const char *env = getenv("NAPAFFT_FUSED_UPG")) G.fused_upg = atoi(env);
+    if (const char *env = getenv("NAPAFFT_FUSED_GRID")) G.fused_grid = atoi(env);
+    if (const char *env = getenv("NAPAFFT_FUSED")) G.use_fused = atoi(env) != 0;
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;

@@ -819,199 +819,158 @@ fft_pass_kernel(const PassParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Group-fused two-pass kernel: ONE launch runs both digit passes of every transform of a batch
-// and the intermediate never leaves L2.  The grid is `ngroups` groups of `gsize` co-resident CTAs
-// (cooperative launch).  A group owns one transform at a time: its CTAs share the pass-A tiles,
-// meet at a group barrier (one arrival counter per group, release/acquire at gpu scope), then
-// share the pass-B tiles, whose loads bypass L1 (ld.global.cg) and hit the lines pass A just
-// wrote.  The live intermediate is ngroups * n * 16 bytes, sized by the host to a fraction of L2.
-//   PK 0: natural order.  A = column digit, src -> the group's scratch slot [k1][n2]; B = row
-//         digit, slot -> dst stored transposed.  A second barrier per transform keeps the next
-//         transform's pass A from overwriting the slot while pass B still reads it.
+// Fused two-pass kernel: ONE persistent cooperative launch runs both digit passes of every
+// transform of a batch; the intermediate lives in L2 between them and every element crosses HBM
+// once in and once out.  (The reference keeps large transforms cache-resident the same way, by
+// recursing depth first: forward.lisp:76-112.)
+//
+// Work is cut into UNITS of `upg` consecutive transforms (about one tile per resident CTA and
+// pass).  The whole grid works through the phases
+//        A(0) A(1) | B(0) B(1) A(2) A(3) | B(2) B(3) A(4) A(5) | ...
+// (A = first digit pass, B = second) as one flat list of tiles dealt round-robin to the CTAs, so
+// that neighbouring CTAs hold neighbouring tiles (DRAM locality) and nobody owns a transform.
+// Dependencies are counters, not barriers: a CTA publishes every finished tile with a release
+// increment of its unit's counter and, before its first B(u) tile, checks that all A(u) tiles are
+// in.  Between A(u) and B(u) lies a whole other phase of work, so that check almost never waits.
+// At most two units of intermediate (<= ~40 MiB) are live at any time.
+//   PK 0: natural order.  A = column digit, src -> ring slot (u & 1) as [k1][n2]; B = row digit,
+//         ring -> dst stored transposed.  A(u) also waits for B(u - 2), the slot's last reader.
 //   PK 1: forward, bit-reversed output.  A = column digit src -> dst, B = row digit in place.
 //   PK 2: inverse of a bit-reversed input. A = row digit src -> dst, B = column digit in place.
+// L2 eviction hints: caller's src / final dst are evict-first streams, the intermediate evict-last.
 // ------------------------------------------------------------------------------------------
 #ifdef NAPA_EMULATE
 #define NAPA_GRID_CONSTANT
 #else
 #define NAPA_GRID_CONSTANT __grid_constant__
 #endif
-struct PipeParams {
-    alignas(64) unsigned long long col_tmap[16];   // CUtensorMap of the column pass's source: [item][row i][2*col] doubles, box = one tile
-    PassParams a, b;                 // pass A (first executed) and pass B
+struct FusedParams {
+    PassParams a, b;                 // pass A (first executed) and pass B, geometry as launch_pass would set it
     long long items;                 // batch
-    int gsize, ngroups;              // CTAs per group, groups (grid = gsize * ngroups)
-    int tiles_a, tiles_b;            // tiles per transform of each pass
-    int a_dst_is_ring, b_src_is_ring;// intermediate lives in scratch slot `group` (else in dst)
-    unsigned *bar;                   // [ngroups][32] arrival counters (one 128-byte line each), zeroed before launch
-    int *error;                      // set to 1 if a barrier wait timed out (never expected)
-    int debug;
+    int upg, nunits;                 // transforms per unit, units
+    unsigned *done_a, *done_b;       // [nunits] finished-tile counters, zeroed before the launch
+    int *error;                      // set to 1 if a wait timed out (never expected)
 };
 
-__host__ __device__ constexpr unsigned pipe_flags_a(int pk) {
-    return pk == 0 ? (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_WIN_REV | PF_CONJ_IN | PF_TW_STORE | PF_RIFFT_PRE)
+__host__ __device__ constexpr unsigned fused_flags_a(int pk) {
+    return pk == 0 ? (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_WIN_REV | PF_CONJ_IN | PF_TW_STORE | PF_ZIP2 | PF_RIFFT_PRE)
          : pk == 1 ? (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_TW_STORE | PF_OUT_REV)
                    : (PF_SCALE | PF_WIN_REAL | PF_WIN_CPLX | PF_CONJ_IN | PF_IN_REV);
 }
-__host__ __device__ constexpr unsigned pipe_flags_b(int pk) {
+__host__ __device__ constexpr unsigned fused_flags_b(int pk) {
     return pk == 0 ? PF_CONJ_OUT : pk == 1 ? PF_OUT_REV : (PF_IN_REV | PF_TW_LOAD | PF_CONJ_OUT);
 }
-__host__ __device__ constexpr int pipe_kind_a(int pk) { return pk == 2 ? 1 : 0; }
-__host__ __device__ constexpr int pipe_kind_b(int pk) { return pk == 0 ? 2 : (pk == 1 ? 1 : 0); }
+// flags a pass carries whatever the call's options are (folded into the instantiation)
+__host__ __device__ constexpr unsigned fused_fixed_a(int pk) {
+    return pk == 0 ? PF_TW_STORE : pk == 1 ? (PF_TW_STORE | PF_OUT_REV) : (PF_CONJ_IN | PF_IN_REV);
+}
+__host__ __device__ constexpr unsigned fused_fixed_b(int pk) {
+    return pk == 0 ? 0u : pk == 1 ? PF_OUT_REV : (PF_IN_REV | PF_TW_LOAD | PF_CONJ_OUT);
+}
+constexpr unsigned FUSED_WINDOW_FLAGS = PF_WIN_REAL | PF_WIN_CPLX | PF_WIN_REV | PF_ZIP2 | PF_RIFFT_PRE;
+__host__ __device__ constexpr int fused_kind_a(int pk) { return pk == 2 ? 1 : 0; }
+__host__ __device__ constexpr int fused_kind_b(int pk) { return pk == 0 ? 2 : (pk == 1 ? 1 : 0); }
+__host__ __device__ constexpr size_t fused_smem_bytes(int la, int lb, int pk) {
+    const size_t a = kind_smem_bytes(la, fused_kind_a(pk)), b = kind_smem_bytes(lb, fused_kind_b(pk));
+    return ((a > b ? a : b) + 127) / 128 * 128;
+}
 
-// All CTAs of a group arrive; returns when `target` arrivals are visible.  Stores issued by any
-// thread of an arriving CTA before the barrier are visible to every thread of a released CTA.
-__device__ __forceinline__ void group_barrier(unsigned *ctr, const unsigned target, int *error) {
-    __syncthreads();
+// geometry of a column-like / row-like digit pass of a two-digit item [2^LCOL][2^LROW], as
+// compile-time constants (the same values pass_geometry() computes on the host)
+template <int LCOL, int LROW> __device__ __forceinline__ void fold_col_geometry(PassParams &q) {
+    constexpr int LC = plan_log2c(LCOL);
+    q.G = 1 << (LROW - LC); q.lg_G = LROW - LC; q.tiles_per_item = q.G; q.lg_tpi = q.lg_G;
+    q.s_SA = 1LL << (LCOL + LROW); q.s_SG = 1 << LC; q.s_i = 1LL << LROW; q.s_q = 1;
+    q.d_SA = q.s_SA; q.d_SG = q.s_SG; q.d_i = q.s_i; q.d_q = q.s_q;
+}
+template <int LCOL, int LROW> __device__ __forceinline__ void fold_row_geometry(PassParams &q) {
+    constexpr int LC = plan_log2c(LROW);
+    q.G = 1; q.lg_G = 0; q.tiles_per_item = 1 << (LCOL - LC); q.lg_tpi = LCOL - LC;
+    q.s_SA = 1LL << (LC + LROW); q.s_SG = 0; q.s_i = 1; q.s_q = 1LL << LROW;
+    q.d_SA = q.s_SA; q.d_SG = q.s_SG; q.d_i = q.s_i; q.d_q = q.s_q;
+}
+
+__device__ __forceinline__ void publish_tile(unsigned *ctr) {
+#ifdef NAPA_EMULATE
+    *ctr += 1;
+#else
+    // release at gpu scope: the CTA's stores (ordered before this thread by the preceding barrier) come first
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(ctr) : "memory");
+#endif
+}
+// thread 0 waits until `target` tiles are in, then the CTA barrier carries the acquire to everyone
+__device__ __forceinline__ void await_tiles(const unsigned *ctr, const unsigned target, int *error) {
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
         unsigned spins = 0;
         while (ld_acquire_u32(ctr) < target) {
-            napa_nanosleep(64);
+            napa_nanosleep(40);
             if (++spins > (1u << 26)) { *error = 1; break; }      // seconds: a lost CTA, never expected
         }
     }
     __syncthreads();
 }
 
-// Warp 0 starts the asynchronous copy of one tile's input into a staging buffer: L rows of C
-// contiguous points (column tile, lane map Q) or C rows of L contiguous points (row tile, map T).
-template <int LOG2L, int LM>
-__device__ __forceinline__ void stage_issue(const PassParams &p, const long long tile, const long long src_item_delta,
-                                            cplx *buf, unsigned long long *mbar, const L2Policies &pol, const void *col_tmap) {
-    constexpr int L = 1 << LOG2L, LC = plan_log2c(LOG2L), C = 1 << LC;
-    const int lane = (int)threadIdx.x & 31;
-    const long long b = tile >> p.lg_tpi;
-    const int r = (int)(tile & (p.tiles_per_item - 1));
-    const int ra = r >> p.lg_G, rg = r & (p.G - 1);
-    const cplx *base = p.src + (b + src_item_delta) * p.src_batch_stride + (long long)ra * p.s_SA + (long long)rg * p.s_SG;
-    fence_proxy_async();           // the buffer's last generic-proxy accesses and (pass B) the other CTAs' stores come first
-    if (lane == 0) mbar_expect_tx(mbar, (unsigned)(L * C * sizeof(cplx)));
-    napa_syncwarp();
-    if (LM == MAP_Q) {
-#ifdef NAPA_EMULATE
-        (void)col_tmap;
-        for (int i = lane; i < L; i += 32) bulk_g2s(buf + (i << LC), base + (long long)i * p.s_i, (unsigned)(C * sizeof(cplx)), mbar, p.src_hint, pol);
-#else
-        // column pass of a two-digit plan: a = 0, the tile is columns [rg*C, rg*C + C) of item b
-        if (lane == 0) tma_tile_g2s(buf, col_tmap, 2 * rg * C, 0, (int)(b + src_item_delta), mbar, p.src_hint, pol);
-#endif
-    } else {
-        for (int q = lane; q < C; q += 32) bulk_g2s(buf + (q << LOG2L), base + (long long)q * p.s_q, (unsigned)(L * sizeof(cplx)), mbar, p.src_hint, pol);
-    }
-}
-
-// Tiles of 2048 points (both digits <= 2^8) are fed by bulk copies, double-buffered: while a CTA
-// computes tile k out of one buffer, the input of its tile k+1 lands in the other, so the global
-// load latency is off the critical path and three CTAs per SM keep the issue slots busy.
-__host__ __device__ constexpr bool pipe_staged(int la, int lb) { return la <= NAPA_SMALL_TILE_MAXL && lb <= NAPA_SMALL_TILE_MAXL; }
-__host__ __device__ constexpr bool pipe_stage_a(int pk) { return pk != 2; }   // PK 2 pass A: bit-reversed rows go through the reorder buffer
-__host__ __device__ constexpr size_t pipe_buf_bytes(int la, int lb, int pk) {
-    const size_t a = kind_smem_bytes(la, pipe_kind_a(pk)), b = kind_smem_bytes(lb, pipe_kind_b(pk));
-    return ((a > b ? a : b) + 127) / 128 * 128;
-}
-__host__ __device__ constexpr size_t pipe_smem_bytes(int la, int lb, int pk) {
-    return pipe_staged(la, lb) ? 2 * pipe_buf_bytes(la, lb, pk) + 16 : pipe_buf_bytes(la, lb, pk);
-}
-__host__ __device__ constexpr int pipe_min_ctas(int la, int lb) { return pipe_staged(la, lb) ? 3 : plan_min_ctas(la); }
-
-template <int LA, int LB, int PK>
-__global__ void __launch_bounds__(plan_threads(LA), pipe_min_ctas(LA, LB)) fft_pipeline_kernel(const NAPA_GRID_CONSTANT PipeParams p) {
+template <int LA, int LB, int PK, bool WIN>
+__global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_fused_kernel(const NAPA_GRID_CONSTANT FusedParams p) {
     static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a fused pair use the same tile shape");
-    constexpr int KA = pipe_kind_a(PK), KB = pipe_kind_b(PK);
-    constexpr bool ST = pipe_staged(LA, LB), STA = ST && pipe_stage_a(PK), STB = ST;
+    constexpr int KA = fused_kind_a(PK), KB = fused_kind_b(PK);
+    constexpr int LGTPI = LA + LB - plan_log2pts(LA);          // tiles per transform and pass
+    constexpr bool RING = PK == 0;
+    constexpr unsigned ALLOW_A = WIN ? fused_flags_a(PK) : (fused_flags_a(PK) & ~FUSED_WINDOW_FLAGS);
     NAPA_DYN_SMEM(cplx, sm);
     const L2Policies pol = make_policies();          // created once per thread, at kernel entry
     NoHook nh;
-    const int g = (int)blockIdx.x / p.gsize, r = (int)blockIdx.x - g * p.gsize;
-    unsigned *ctr = p.bar + 32 * g;
-    unsigned arrivals = 0;
-    if constexpr (!ST) {
-        for (long long item = g; item < p.items; item += p.ngroups) {
-            const long long delta = (long long)g - item;
-            bool first = true;
-            for (int t = r; t < p.tiles_a; t += p.gsize) {
-                if (!first) __syncthreads();       // previous tile is done with sm
-                first = false;
-                run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, pipe_flags_a(PK)>(
-                    p.a, item * p.tiles_a + t, sm, 0, p.a_dst_is_ring ? delta : 0, pol, nh);
+    // local copies of the pass descriptions with everything the instantiation knows folded in
+    PassParams pa = p.a, pb = p.b;
+    if (PK == 2) { fold_row_geometry<LB, LA>(pa); fold_col_geometry<LB, LA>(pb); }
+    else         { fold_col_geometry<LA, LB>(pa); fold_row_geometry<LA, LB>(pb); }
+    if (PK == 0) { pb.d_SA = 1 << plan_log2c(LB); pb.d_SG = 0; pb.d_i = 1LL << LA; pb.d_q = 1; }
+    pa.flags = (p.a.flags & ~fused_fixed_a(PK) & ALLOW_A) | fused_fixed_a(PK);
+    pb.flags = (p.b.flags & ~fused_fixed_b(PK) & fused_flags_b(PK)) | fused_fixed_b(PK);
+    pa.src_hint = HINT_STREAM; pa.dst_hint = HINT_KEEP; pb.src_hint = HINT_KEEP; pb.dst_hint = HINT_STREAM;
+    pa.lgN = LA + LB; pb.lgN = LA + LB;
+
+    const long long G = (long long)gridDim.x, c = (long long)blockIdx.x;
+    const long long tfull = (long long)p.upg << LGTPI;          // tiles per full unit and pass
+    int known_a = -1, known_b = -1;                               // newest unit whose pass is known to be complete
+    unsigned *pending = nullptr;                                  // counter owed one increment for the tile just stored
+    long long base = 0;                                           // flat slot of the phase's first tile
+    const int nphases = 2 * p.nunits;
+    for (int ph = 0; ph < nphases; ph++) {
+        // phase list = A0 A1 B0 B1 | A2 A3 B2 B3 | ...
+        int u; bool is_b;
+        {
+            const int q4 = ph >> 2, r4 = ph & 3;
+            is_b = r4 >= 2; u = 2 * q4 + (r4 & 1);
+            if (u >= p.nunits) {
+                // an odd unit count: the last block is A(u0) B(u0) with u0 = nunits - 1
+                const int u0 = p.nunits - 1;
+                is_b = ((ph - 4 * (u0 >> 1)) & 1) != 0; u = u0;
             }
-            arrivals += (unsigned)p.gsize;
-            group_barrier(ctr, arrivals, p.error);
-            first = true;
-            for (int t = r; t < p.tiles_b; t += p.gsize) {
-                if (!first) __syncthreads();
-                first = false;
-                run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, NoHook, pipe_flags_b(PK)>(
-                    p.b, item * p.tiles_b + t, sm, p.b_src_is_ring ? delta : 0, 0, pol, nh);
-            }
-            if (PK == 0) {                          // the slot is rewritten by the next transform's pass A
-                arrivals += (unsigned)p.gsize;
-                group_barrier(ctr, arrivals, p.error);
+        }
+        const long long left = p.items - (long long)u * p.upg;
+        const long long tu = (left < p.upg ? left : (long long)p.upg) << LGTPI;
+        long long s = base + ((c - base % G) + G) % G;
+        for (; s < base + tu; s += G) {
+            const long long tile = (long long)u * tfull + (s - base);
+            __syncthreads();                             // the previous tile is done with sm and has issued its stores
+            if (threadIdx.x == 0 && pending) publish_tile(pending);
+            pending = nullptr;
+            const long long ring_delta = RING ? ((long long)(u & 1) - u) * p.upg : 0;
+            if (!is_b) {
+                if (RING && u >= 2 && u - 2 > known_b) { await_tiles(p.done_b + (u - 2), (unsigned)tfull, p.error); known_b = u - 2; }
+                run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, ALLOW_A>(pa, tile, sm, 0, ring_delta, pol, nh);
+                pending = p.done_a + u;
             } else {
-                __syncthreads();
+                if (u > known_a) { await_tiles(p.done_a + u, (unsigned)tu, p.error); known_a = u; }
+                run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, NoHook, fused_flags_b(PK)>(pb, tile, sm, ring_delta, 0, pol, nh);
+                pending = RING ? p.done_b + u : nullptr;
             }
         }
-    } else {
-        constexpr size_t BUF = pipe_buf_bytes(LA, LB, PK) / sizeof(cplx);
-        unsigned long long *mbar = reinterpret_cast<unsigned long long *>(sm + 2 * BUF);
-        if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); fence_proxy_async(); }
-        __syncthreads();
-        const int nA = (p.tiles_a - r + p.gsize - 1) / p.gsize, nB = (p.tiles_b - r + p.gsize - 1) / p.gsize;
-        const bool warp0 = threadIdx.x < 32;
-        unsigned parity = 0;                   // bit b: phase parity of mbar[b]
-        int k = 0;                             // tiles done by this CTA: tile k lives in buf[k & 1]
-        bool have = false;                     // the current tile's input is already on its way
-        for (long long item = g; item < p.items; item += p.ngroups) {
-            const long long delta = (long long)g - item;
-            for (int s = 0; s < nA + nB; s++, k++) {
-                const bool is_a = s < nA;
-                // barriers: before the first B tile (the group's A output is complete), and for the
-                // scratch slot of PK 0 before the next transform's A tiles store into it
-                if (s == nA || (PK == 0 && s == 0 && item != (long long)g)) {
-                    arrivals += (unsigned)p.gsize;
-                    group_barrier(ctr, arrivals, p.error);
-                } else {
-                    __syncthreads();               // previous tile is done with both buffers' generic accesses
-                }
-                const int cb = k & 1, nb = cb ^ 1;
-                // the tile after this one
-                int s2 = s + 1; long long item2 = item;
-                if (s2 == nA + nB) { s2 = 0; item2 += p.ngroups; }
-                const bool next_exists = item2 < p.items;
-                const bool next_a = s2 < nA;
-                // not across the A -> B barrier (the data is not there yet), and only staged passes
-                const bool prefetch = next_exists && s2 != nA && (next_a ? STA : STB);
-                if (warp0) {
-                    if (!have) {
-                        if (is_a) { if constexpr (STA) stage_issue<LA, kind_lm(LA, KA)>(p.a, item * p.tiles_a + r + s * p.gsize, 0, (sm + cb * BUF), mbar + cb, pol, p.col_tmap); }
-                        else stage_issue<LB, kind_lm(LB, KB)>(p.b, item * p.tiles_b + r + (s - nA) * p.gsize, p.b_src_is_ring ? delta : 0, (sm + cb * BUF), mbar + cb, pol, p.col_tmap);
-                    }
-                    if (prefetch) {
-                        const long long delta2 = (long long)g - item2;
-                        if (next_a) { if constexpr (STA) stage_issue<LA, kind_lm(LA, KA)>(p.a, item2 * p.tiles_a + r + s2 * p.gsize, 0, (sm + nb * BUF), mbar + nb, pol, p.col_tmap); }
-                        else stage_issue<LB, kind_lm(LB, KB)>(p.b, item2 * p.tiles_b + r + (s2 - nA) * p.gsize, p.b_src_is_ring ? delta2 : 0, (sm + nb * BUF), mbar + nb, pol, p.col_tmap);
-                    }
-                }
-                if (is_a) {
-                    if constexpr (STA) {
-                        run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, true, NoHook, pipe_flags_a(PK), true, true>(
-                            p.a, item * p.tiles_a + r + s * p.gsize, (sm + cb * BUF), 0, p.a_dst_is_ring ? delta : 0, pol, nh, mbar + cb, (parity >> cb) & 1u);
-                        parity ^= 1u << cb;
-                    } else {
-                        run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, pipe_flags_a(PK)>(
-                            p.a, item * p.tiles_a + r + s * p.gsize, (sm + cb * BUF), 0, p.a_dst_is_ring ? delta : 0, pol, nh);
-                    }
-                } else {
-                    run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, true, NoHook, pipe_flags_b(PK), true, true>(
-                        p.b, item * p.tiles_b + r + (s - nA) * p.gsize, (sm + cb * BUF), p.b_src_is_ring ? delta : 0, 0, pol, nh, mbar + cb, (parity >> cb) & 1u);
-                    parity ^= 1u << cb;
-                }
-                have = prefetch;
-            }
-        }
+        base += tu;
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && pending) publish_tile(pending);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
-"""Runs two-digit transforms through the group-fused two-pass kernel (NAPAFFT_PIPELINE is read
-at library init, hence a separate process).  argv[1]: "emul" (CPU emulation build) or "gpu"."""
+"""Runs two-digit transforms (2^14 .. 2^20: the fused single-launch kernel unless NAPAFFT_FUSED=0; the
+tuning variables NAPAFFT_FUSED* are read at library init, hence a separate process).
+argv[1]: "emul" (CPU emulation build) or "gpu"."""
 import os
 import sys
 
@@ -14,12 +15,12 @@ if sys.argv[1] == "emul":
     from napa_fft3_b200 import Binding, NapaFFT
     b = Binding(build()); b.init(0)
     napa = NapaFFT(b)
-    sizes, batch = (14, 16), 5
+    sizes, batch = (14, 15), 5
 else:
     import napa_fft3_b200 as P
     P.default_binding()
     napa = P._default
-    sizes, batch = (14, 16, 20, 22), 9
+    sizes, batch = (14, 15, 16, 18, 19, 20, 22), 9
 for lg in sizes:
     n = 1 << lg
     for io in (True, False):
@@ -31,8 +32,11 @@ for lg in sizes:
         assert max(S.nre(got[i], O.fft(x[i], in_order=io)) for i in range(batch)) <= S.tol(n)
         back = napa.fft_batch(got, direction=-1, in_order=io, scale=True)
         assert S.nre(back, x) <= S.tol(n)
+    # the real wrappers ride on the same plans (zip / rifft pre-twiddle fused into the first pass)
+    S.check_2rfft(napa, n)
+    S.check_real(napa, 2 * n, "sqrt")
 if sys.argv[1] != "emul":
-    # more transforms than groups: every group loops over several transforms (slot reuse, barrier epochs)
+    # many units per launch: ring-slot reuse, ragged last unit, every CTA crossing many phases
     for lg, batch in ((14, 1500), (16, 333), (18, 70)):
         n = 1 << lg
         rng = np.random.Generator(np.random.Philox(lg))
@@ -43,4 +47,4 @@ if sys.argv[1] != "emul":
                 assert S.nre(got[i], O.fft(x[i], in_order=io)) <= S.tol(n), (lg, io, i)
             back = napa.fft_batch(got, direction=-1, in_order=io, scale=True)
             assert S.nre(back, x) <= S.tol(n), (lg, io)
-print("pipeline ok")
+print("fused ok")

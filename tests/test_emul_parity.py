@@ -117,17 +117,18 @@ def test_many_tiles_single_pass(napa, n, batch):
     assert S.nre(back, x * w) < 1e-13
 
 
-def test_optional_l2_pipeline_path():
-    """the group-fused two-pass kernel (off by default, NAPAFFT_PIPELINE=1) stays correct: real multi-CTA groups
-    (the emulator keeps every CTA of a cooperative launch alive, tests/emul/cuda_emul.cpp: launch_cooperative),
-    group barriers, scratch-slot reuse across a group's transforms, staged tiles, natural and bit-reversed plans;
-    groups of 4 CTAs (several tiles per CTA and phase) and of 8 (one tile per CTA and phase at 2^14)"""
+def test_fused_kernel_schedules():
+    """the fused single-launch kernel (default for 2^14 .. 2^20) under several schedules: the emulator keeps every CTA
+    of a cooperative launch alive (tests/emul/cuda_emul.cpp: launch_cooperative), so the tile counters, the waits on
+    them, ring-slot reuse, ragged last units and odd unit counts all really run; and the same cases with the fused
+    plans switched off (one launch per digit pass)"""
     import subprocess
-    for extra in ({}, {"NAPAFFT_PIPE_GSIZE": "8"}):
-        env = dict(os.environ, NAPAFFT_PIPELINE="1", **extra)
-        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
+    for extra in ({}, {"NAPAFFT_FUSED_UPG": "1", "NAPAFFT_FUSED_GRID": "2"}, {"NAPAFFT_FUSED_UPG": "3", "NAPAFFT_FUSED_GRID": "5"},
+                  {"NAPAFFT_FUSED": "0"}):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_probe.py"), "emul"],
                              env=env, capture_output=True, text=True, timeout=1200)
-        assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        assert out.returncode == 0 and "fused ok" in out.stdout, str(extra) + out.stdout[-2000:] + out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("digits,n", [("5,5,6", 1 << 16), ("7,8", 1 << 15), ("6,5,6", 1 << 17)])
@@ -158,10 +159,9 @@ def test_natural_order_in_place_fallback():
     bit-reversed pipeline + bit-reversal pass; forced here at small sizes with NAPAFFT_MAX_SCRATCH_KB"""
     import subprocess
     env = dict(os.environ, NAPAFFT_MAX_SCRATCH_KB="1")
-    env.pop("NAPAFFT_PIPELINE", None)
-    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "emul"],
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_probe.py"), "emul"],
                          env=env, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_golden_vectors(napa):

@@ -188,15 +188,16 @@ def test_distributed_building_blocks_single_rank(napa, lgN):
     assert S.nre(back.cpu().numpy().reshape(-1), x.reshape(f.N1, f.N2).reshape(-1)) <= S.tol(1 << lgN)
 
 
-def test_optional_l2_pipeline_path_gpu():
-    """group-fused two-pass kernel (NAPAFFT_PIPELINE=1): automatic group shape, narrow groups (several tiles
-    per CTA and phase: the staged prefetch chain) and wide groups (one tile per CTA and phase)"""
+def test_fused_kernel_schedules_gpu():
+    """fused single-launch kernel (default for 2^14 .. 2^20): automatic unit / grid shape, one transform per unit on a
+    small grid (every CTA crosses many phases and really waits on the counters), wide units, and the same cases
+    with the fused plans off (one launch per digit pass)"""
     import subprocess
-    for extra in ({}, {"NAPAFFT_PIPE_GSIZE": "4"}, {"NAPAFFT_PIPE_GSIZE": "32", "NAPAFFT_PIPE_L2_MB": "8"}):
-        env = dict(os.environ, NAPAFFT_PIPELINE="1", **extra)
-        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py"), "gpu"],
+    for extra in ({}, {"NAPAFFT_FUSED_UPG": "1", "NAPAFFT_FUSED_GRID": "37"}, {"NAPAFFT_FUSED_UPG": "5"}, {"NAPAFFT_FUSED": "0"}):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_probe.py"), "gpu"],
                              env=env, capture_output=True, text=True, timeout=600)
-        assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        assert out.returncode == 0 and "fused ok" in out.stdout, str(extra) + out.stdout[-2000:] + out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("n,chunk", [(1000, 64), (100000, 1024), (777, 1024), (5000, 2), (1 << 20, 1 << 16), (300001, 4096)])
