@@ -15,30 +15,38 @@
     (sequence (map-into (make-array size :element-type 'real-sample)
                         (lambda (x) (coerce x 'real-sample)) vec))))
 
-(defun copy-or-replace (src dst)                              ; easy-interface.lisp:3-8
-  (cond ((eql src dst) dst) (dst (replace dst src)) (t (copy-seq src))))
+;;; Aliasing contract of the easy interface (easy-interface.lisp:3-8, 44-57, 69-82 of the reference; it is
+;;; part of the public behaviour and must not change): the transform runs in place on DST when DST is
+;;; given (after copying the input there), in place on a FRESH vector when the caller's VEC had to be
+;;; converted, and on a copy of VEC otherwise -- the caller's own complex-sample-array is never clobbered
+;;; unless it is passed as :dst.
+(defun copy-or-replace (src dst)
+  (cond ((eql src dst) dst)
+        (dst (replace dst src))
+        (t (copy-seq src))))
+
+(defun transform-target (vec dst n)
+  "The vector a transform of the first N samples of VEC works on (see the aliasing contract above)."
+  (let* ((samples (complex-samplify vec n))
+         (target (if (or dst (eql samples vec))
+                     (copy-or-replace samples dst)
+                     samples)))             ; already a private conversion of the caller's sequence
+    (assert (power-of-two-p n))
+    (assert (>= (length samples) n))
+    (assert (>= (length target) n))
+    target))
 
 (defun fft (vec &key dst size (in-order t) (scale nil) (window nil))
   (declare (type (or null complex-sample-array) dst))
   (let* ((n (or size (length vec)))
-         (old vec)
-         (vec (complex-samplify vec n))
-         (dst (if (or (eql old vec) dst) (copy-or-replace vec dst) vec)))
-    (assert (power-of-two-p n))
-    (assert (>= (length vec) n))
-    (assert (>= (length dst) n))
-    (%c2c dst dst n 0 1 (scale-code scale) in-order window 0)))
+         (target (transform-target vec dst n)))
+    (%c2c target target n 0 1 (scale-code scale) in-order window 0)))
 
 (defun ifft (vec &key dst size (in-order t) (scale t) (window nil))
   (declare (type (or null complex-sample-array) dst))
   (let* ((n (or size (length vec)))
-         (old vec)
-         (vec (complex-samplify vec n))
-         (dst (if (or (eql old vec) dst) (copy-or-replace vec dst) vec)))
-    (assert (power-of-two-p n))
-    (assert (>= (length vec) n))
-    (assert (>= (length dst) n))
-    (%c2c dst dst n 0 -1 (scale-code scale) in-order window 0)))
+         (target (transform-target vec dst n)))
+    (%c2c target target n 0 -1 (scale-code scale) in-order window 0)))
 
 (defun bit-reverse (vec &optional dst (size (length vec)))
   (let ((elt (etypecase vec (complex-sample-array 0) (real-sample-array 1)))

@@ -60,23 +60,21 @@
   (etypecase window
     (null 0) (real-sample-array 1) (complex-sample-array 2)))
 
-(defun sap+ (vector start bytes-per-element)
-  (sap+ (vector-sap vector) (* start bytes-per-element)))
+(declaim (inline element-sap))
+(defun element-sap (vector index bytes-per-element)
+  "Address of element INDEX of a specialised vector.  Only valid inside WITH-PINNED-OBJECTS."
+  (sb-sys:sap+ (sb-sys:vector-sap vector) (* index bytes-per-element)))
 
 (defun %c2c (src dst n start dir scale in-order window window-start)
   "Transform SRC[start, start+n) into DST[start, start+n)."
   (declare (type complex-sample-array src dst))
-  (let ((null-sap (int-sap 0)))
-    (if window
-        (with-pinned-objects (src dst window)
-          (check (napafft-c2c (sb-sys:sap+ (vector-sap src) (* 16 start))
-                              (sb-sys:sap+ (vector-sap dst) (* 16 start))
-                              n 1 n dir scale (if in-order 1 0)
-                              (sb-sys:sap+ (vector-sap window)
-                                           (* (if (typep window 'real-sample-array) 8 16) window-start))
-                              (window-code window) 0)))
-        (with-pinned-objects (src dst)
-          (check (napafft-c2c (sb-sys:sap+ (vector-sap src) (* 16 start))
-                              (sb-sys:sap+ (vector-sap dst) (* 16 start))
-                              n 1 n dir scale (if in-order 1 0) null-sap 0 0)))))
+  (if window
+      (with-pinned-objects (src dst window)
+        (check (napafft-c2c (element-sap src start 16) (element-sap dst start 16)
+                            n 1 n dir scale (if in-order 1 0)
+                            (element-sap window window-start (if (typep window 'real-sample-array) 8 16))
+                            (window-code window) 0)))
+      (with-pinned-objects (src dst)
+        (check (napafft-c2c (element-sap src start 16) (element-sap dst start 16)
+                            n 1 n dir scale (if in-order 1 0) (sb-sys:int-sap 0) 0 0))))
   dst)
