@@ -82,7 +82,10 @@ struct State {
     size_t max_scratch_bytes = (size_t)16 << 30;   // natural-order scratch copy up to this size, else in-place fallback
     size_t fused_unit_bytes = 20u << 20;  // fused kernel: largest unit of intermediate (two units are live in L2)
     int fused_upg = 0, fused_grid = 0;    // tuning overrides: transforms per unit, CTAs (0 = auto)
-    bool use_fused = true;                // fused single-launch plans for 2^14 .. 2^20 (NAPAFFT_FUSED=0: one launch per digit pass)
+    int fused_prefetch = 1;               // L2 prefetch of each CTA's next pass-A tile
+    int fused_tma = 0;                    // NAPAFFT_FUSED_TMA=1: TMA-fed warp-specialised variant of the fused kernel (2^14 .. 2^16)
+    int fused_lead = 0;                   // units pass A runs ahead of pass B (0 = default 2)
+    bool use_fused = false;               // fused single-launch plans for 2^14 .. 2^20 (NAPAFFT_FUSED=1); measured: no faster than one launch per digit pass
     bool attrs_set = false;
     int num_sms = 148;
     std::map<cudaStream_t, std::pair<unsigned char *, size_t>> counters;   // per-stream group-barrier counters
@@ -272,6 +275,43 @@ static fused_fn fused_kernel(int la, int lb, int pk, bool win) {
     NAPA_FUSED_CASE(9, 9) NAPA_FUSED_CASE(9, 10) NAPA_FUSED_CASE(10, 9) NAPA_FUSED_CASE(10, 10)
     return nullptr;
 }
+typedef void (*fused_tma_fn)(const napa::FusedTmaParams);
+#define NAPA_FUSED_TMA_CASE(a, b)                                                                 \
+    if (la == a && lb == b) {                                                                     \
+        if (win) return pk == 0 ? napa::fft_fused_tma_kernel<a, b, 0, true> : (pk == 1 ? napa::fft_fused_tma_kernel<a, b, 1, true> : napa::fft_fused_tma_kernel<a, b, 2, true>); \
+        return pk == 0 ? napa::fft_fused_tma_kernel<a, b, 0, false> : (pk == 1 ? napa::fft_fused_tma_kernel<a, b, 1, false> : napa::fft_fused_tma_kernel<a, b, 2, false>); \
+    }
+// TMA-fed variant: 2048-point tiles only (a column tile is one tensor-map box of <= 256 rows)
+static fused_tma_fn fused_tma_kernel(int la, int lb, int pk, bool win) {
+    NAPA_FUSED_TMA_CASE(7, 7) NAPA_FUSED_TMA_CASE(7, 8) NAPA_FUSED_TMA_CASE(8, 7) NAPA_FUSED_TMA_CASE(8, 8)
+    return nullptr;
+}
+#ifndef NAPA_EMULATE
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// tensor map of a column pass's operand: doubles [item][row i][2 * col], one box = one tile = L rows x C columns
+static int encode_col_tmap(unsigned long long *out, const PassParams &cp, int l, long long items) {
+    static tmap_encode_fn enc = nullptr;
+    if (!enc) {
+        void *fp = nullptr; cudaDriverEntryPointQueryResult qr;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr));
+        if (!fp || qr != cudaDriverEntryPointSuccess) return fail(NAPA_E_CUDA, "cuTensorMapEncodeTiled is not available");
+        enc = (tmap_encode_fn)fp;
+    }
+    const cuuint64_t B = (cuuint64_t)cp.s_i, L = 1ull << l, C = 1ull << napa::plan_log2c(l);
+    const cuuint64_t gdim[3] = { 2 * B, L, (cuuint64_t)items };
+    const cuuint64_t gstr[2] = { B * sizeof(cplx), (cuuint64_t)cp.src_batch_stride * sizeof(cplx) };
+    const cuuint32_t box[3] = { (cuuint32_t)(2 * C), (cuuint32_t)L, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult cr = enc((CUtensorMap *)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)cp.src, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(NAPA_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return NAPA_OK;
+}
+#endif
+
 // column digit of the fused plan for 2^lg (0 = no fused kernel: the digits would need two tile shapes,
 // or two units of intermediate would not fit in L2)
 static int fused_col_digit(int lg) {
@@ -311,13 +351,13 @@ static int check_device_error() {
 }
 
 // resident CTAs of a fused kernel (cached)
-static int fused_resident(fused_fn fn, int threads, size_t smem, long long *out) {
-    static std::map<fused_fn, int> occ;
+static int fused_resident(const void *fn, int threads, size_t smem, long long *out) {
+    static std::map<const void *, int> occ;
     auto it = occ.find(fn);
     if (it == occ.end()) {
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, threads, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem));
         if (nb < 1) return fail(NAPA_E_CUDA, "fused kernel does not fit on an SM");
         it = occ.emplace(fn, nb).first;
     }
@@ -331,6 +371,9 @@ static int launch_fused(int la, int lb, int pk, bool win, size_t n, size_t batch
                         cudaStream_t st) {
     fused_fn fn = fused_kernel(la, lb, pk, win);
     if (!fn) return fail(NAPA_E_UNSUPPORTED, "no fused kernel for digits (%d, %d)", la, lb);
+    // TMA-fed warp-specialised variant where it exists; real-input fusions (zip, rifft pre-twiddle) read two operands
+    // per point and stay on the direct-load kernel
+    fused_tma_fn tfn = G.fused_tma && !(fp.a.flags & (napa::PF_ZIP2 | napa::PF_RIFFT_PRE)) ? fused_tma_kernel(la, lb, pk, win) : nullptr;
     OK(check_device_error());
     OK(ensure_stage_tw(la));
     OK(ensure_stage_tw(lb));
@@ -338,10 +381,10 @@ static int launch_fused(int la, int lb, int pk, bool win, size_t n, size_t batch
     fp.b.stage_tw = G.stage_tw[lb];
     fp.a.lg_tpi = ilog2((size_t)fp.a.tiles_per_item); fp.a.lg_G = ilog2((size_t)fp.a.G);
     fp.b.lg_tpi = ilog2((size_t)fp.b.tiles_per_item); fp.b.lg_G = ilog2((size_t)fp.b.G);
-    const size_t smem = napa::fused_smem_bytes(la, lb, pk);
-    const int threads = napa::plan_threads(la);
+    const size_t smem = tfn ? napa::fused_tma_smem_bytes(la, lb, pk) : napa::fused_smem_bytes(la, lb, pk);
+    const int threads = napa::plan_threads(la) + (tfn ? 32 : 0);
     long long W;
-    OK(fused_resident(fn, threads, smem, &W));
+    OK(fused_resident(tfn ? (const void *)tfn : (const void *)fn, threads, smem, &W));
     if (G.fused_grid > 0) W = std::min<long long>(W, G.fused_grid);
     const long long tpi = (long long)(n >> napa::plan_log2pts(la));
     long long upg = std::max<long long>(1, (W + tpi - 1) / tpi);
@@ -356,10 +399,11 @@ static int launch_fused(int la, int lb, int pk, bool win, size_t n, size_t batch
     const long long nunits = ((long long)batch + upg - 1) / upg;
     if (nunits > 0x3fffffffLL) return fail(NAPA_E_UNSUPPORTED, "batch too large for one fused launch");
     fp.items = (long long)batch; fp.upg = (int)upg; fp.nunits = (int)nunits;
+    fp.lead = std::max(1, G.fused_lead > 0 ? G.fused_lead : (tfn ? 2 : 2));
     if (ring) {
-        // natural order: the intermediate of units u and u + 1 (ring slots u & 1)
+        // natural order: ring of lead + 1 unit-sized slots for the intermediate
         cplx *buf;
-        OK(ensure_scratch(st, (size_t)(2 * upg) * n * sizeof(cplx), &buf));
+        OK(ensure_scratch(st, (size_t)((fp.lead + 1) * upg) * n * sizeof(cplx), &buf));
         fp.a.dst = buf; fp.b.src = buf;
     }
     const size_t cbytes = (size_t)nunits * 2 * sizeof(unsigned);
@@ -368,7 +412,22 @@ static int launch_fused(int la, int lb, int pk, bool win, size_t n, size_t batch
     CU(cudaMemsetAsync(ctr, 0, cbytes, st));
     fp.done_a = (unsigned *)ctr; fp.done_b = fp.done_a + nunits;
     fp.error = G.d_error;
+    fp.prefetch = G.fused_prefetch;
     const unsigned grid = (unsigned)std::min<long long>(W, std::max<long long>(1, upg * tpi));
+    if (tfn) {
+        napa::FusedTmaParams tp{};
+        tp.f = fp;
+#ifndef NAPA_EMULATE
+        if (pk == 2) OK(encode_col_tmap(tp.tmap_b, fp.b, lb, (long long)batch));
+        else OK(encode_col_tmap(tp.tmap_a, fp.a, la, (long long)batch));
+        void *args[] = { (void *)&tp };
+        CU(cudaLaunchCooperativeKernel((const void *)tfn, dim3(grid), dim3(threads), args, smem, st));
+#else
+        NAPA_LAUNCH_COOP(tfn, grid, threads, smem, st, tp);
+#endif
+        g_launches++;
+        return NAPA_OK;
+    }
 #ifdef NAPA_EMULATE
     NAPA_LAUNCH_COOP(fn, grid, threads, smem, st, fp);
 #else
@@ -634,6 +693,8 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     }
 
     // bit-reversed pipelines (in place on dst after the first pass), any number of digits
+    if (natural && inv && o.rifft_pre)
+        return fail(NAPA_E_UNSUPPORTED, "rifft of 2^%d points needs a scratch copy of %zu bytes (NAPAFFT_MAX_SCRATCH_KB)", lg + 1, chunk * n * sizeof(cplx));
     if (natural && inv) {
         // reference order: bit-reverse first, then DIT (easy-interface.lisp:83-95)
         OK(exec_bitrev(src, dst, n, batch, sstride, dstride, NAPA_ELT_COMPLEX, st));
@@ -650,6 +711,10 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             pp.dst = dst + b0 * dstride;
             pp.src_batch_stride = (long long)(first ? sstride : dstride); pp.dst_batch_stride = (long long)dstride;
             pp.batch = (long long)nb;
+            if (first && o.zip_im) {   // %2rfft: src is a vector of doubles (strides in doubles), zipped with o.zip_im on the first load
+                pp.src = (const cplx *)((const double *)src + b0 * sstride);
+                pp.flags |= napa::PF_ZIP2; pp.src_im = o.zip_im + b0 * sstride;
+            }
             int lgB = 0;
             for (int i = s + 1; i < p; i++) lgB += d[i];
             if (lgB > 0) {
@@ -1093,6 +1158,10 @@ NAPA_API int napafft_init(int device) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(NAPA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    // tunables: defaults first (a re-init after napafft_shutdown must not inherit the previous settings)
+    { State d; G.chunk_bytes = d.chunk_bytes; G.zero_copy_bytes = d.zero_copy_bytes; G.max_scratch_bytes = d.max_scratch_bytes;
+      G.fused_unit_bytes = d.fused_unit_bytes; G.fused_upg = d.fused_upg; G.fused_grid = d.fused_grid; G.use_fused = d.use_fused;
+      G.fused_prefetch = d.fused_prefetch; G.fused_tma = d.fused_tma; G.fused_lead = d.fused_lead; }
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_ZERO_COPY_KB")) G.zero_copy_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_MAX_SCRATCH_KB")) G.max_scratch_bytes = (size_t)atoll(env) << 10;
@@ -1100,6 +1169,9 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_FUSED_UPG")) G.fused_upg = atoi(env);
     if (const char *env = getenv("NAPAFFT_FUSED_GRID")) G.fused_grid = atoi(env);
     if (const char *env = getenv("NAPAFFT_FUSED")) G.use_fused = atoi(env) != 0;
+    if (const char *env = getenv("NAPAFFT_FUSED_PREFETCH")) G.fused_prefetch = atoi(env);
+    if (const char *env = getenv("NAPAFFT_FUSED_TMA")) G.fused_tma = atoi(env);
+    if (const char *env = getenv("NAPAFFT_FUSED_LEAD")) G.fused_lead = atoi(env);
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;

@@ -22,7 +22,7 @@
 #else
 #include <cuda_runtime.h>
 #define NAPA_DYN_SMEM(T, name)                                      \
-    extern __shared__ __align__(16) unsigned char name##_raw[];    \
+    extern __shared__ __align__(128) unsigned char name##_raw[];    \
     T *name = reinterpret_cast<T *>(name##_raw)
 #define NAPA_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
@@ -211,16 +211,32 @@ __device__ __forceinline__ L2Policies make_policies() { return L2Policies{0}; }
 template <bool COHERENT> __device__ __forceinline__ cplx ld_data(const cplx *p, int, const L2Policies &) { return *p; }
 __device__ __forceinline__ void st_data(cplx *p, cplx v, int, const L2Policies &) { *p = v; }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
+__device__ __forceinline__ void fence_acq_rel_gpu() {}
 __device__ __forceinline__ void napa_nanosleep(unsigned) { napa_emul::yield_spin(); }   // let the other CTAs' fibers run
-// bulk-copy staging: the emulator copies synchronously and never waits
-__device__ __forceinline__ void mbar_init(unsigned long long *, unsigned) {}
+// mbarriers and bulk copies, emulated: a copy is done synchronously at issue time and the barrier's
+// transaction count is ignored, so the issuing thread's expect_tx arrival is deferred to mbar_emul_complete()
+// (called right after the copies; a no-op on the device).  Word layout: [63] phase, [62:32] count, [31:0] pending.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { *bar = ((unsigned long long)count << 32) | count; }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    unsigned long long w = *bar;
+    unsigned pending = (unsigned)w - 1;
+    const unsigned long long count = (w >> 32) & 0x7fffffffull, phase = w >> 63;
+    if (pending == 0) w = ((phase ^ 1ull) << 63) | (count << 32) | count;
+    else w = (phase << 63) | (count << 32) | pending;
+    *bar = w;
+    napa_emul::note_progress();
+}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *, unsigned) {}
-__device__ __forceinline__ void mbar_wait(unsigned long long *, unsigned) { __syncthreads(); }   // every thread waits once per staged tile
+__device__ __forceinline__ void mbar_emul_complete(unsigned long long *bar) { mbar_arrive(bar); }
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) { return (unsigned)(*(volatile unsigned long long *)bar >> 63) != parity; }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) { while (!mbar_test(bar, parity)) napa_emul::yield_any(); }
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void napa_syncwarp() {}
 __device__ __forceinline__ void bulk_g2s(cplx *s, const cplx *g, unsigned bytes, unsigned long long *, int, const L2Policies &) {
     for (unsigned i = 0; i < bytes / sizeof(cplx); i++) s[i] = g[i];
 }
+template <int N> struct SyncCompute { static __device__ __forceinline__ void sync() { napa_emul::bar_sync(1, N); } };
 #else
 struct L2Policies { unsigned long long normal, first, last; };
 __device__ __forceinline__ L2Policies make_policies() {
@@ -254,6 +270,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void napa_nanosleep(unsigned ns) { __nanosleep(ns); }
 // mbarrier + bulk asynchronous copy (TMA engine, no tensor map): global -> shared, completion
 // counted in bytes on an mbarrier.  The copy goes through L2 only, hence sees other SMs' writes.
@@ -263,16 +285,22 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_emul_complete(unsigned long long *) {}
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "NAPA_MBAR_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra NAPA_MBAR_DONE;\n\t"
-        "bra NAPA_MBAR_WAIT;\n\t"
-        "NAPA_MBAR_DONE:\n\t"
-        "}" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    while (!mbar_test(bar, parity)) {}
 }
 // orders earlier generic-proxy accesses (made visible to this thread) before its later async-proxy operations
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -289,6 +317,10 @@ __device__ __forceinline__ void bulk_g2s(cplx *s, const cplx *g, unsigned bytes,
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  :: "r"((unsigned)__cvta_generic_to_shared(s)), "l"(g), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)), "l"(policy) : "memory");
 }
+#endif
+#ifndef NAPA_EMULATE
+// barrier over the N compute threads of a warp-specialised CTA (named barrier 1; the producer warp stays out)
+template <int N> struct SyncCompute { static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, %0;" :: "n"(N) : "memory"); } };
 #endif
 struct SyncAll { static __device__ __forceinline__ void sync() { __syncthreads(); } };
 
@@ -392,7 +424,12 @@ __device__ __forceinline__ void twiddle_powers(cplx (&v)[16], const int u, const
 // Stockham autosort stages.  Stage 0 runs under the load-side ids (t0, q0) and scatters; every
 // later stage gathers and runs under the store-side ids (t1, q1).  PRESYNC0: sm was used before
 // stage 0 (reorder of a bit-reversed load) and everyone must be done with it before the scatter.
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
+// Hook protocol of run_tile: loads_issued() runs right after the tile's global loads have been issued (their
+// latency hides whatever it does), operator() after the last exchange has been gathered.
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+    __device__ __forceinline__ void loads_issued() const {}
+};
 
 template <int LOG2L, int STAGE, int LOG2NS, bool PLANAR, bool PRESYNC0, class Sync, class Hook>
 struct Stages {
@@ -404,8 +441,15 @@ struct Stages {
     static constexpr int NB = 16 / R;
     static constexpr int NS = 1 << LOG2NS;
 
+    // seed of butterfly u of this stage (thread position t on the store side): W_{NS*R}^{(t + u*T) % NS}
+    static __device__ __forceinline__ cplx load_seed(const cplx *__restrict__ tw, const int t, const int u) {
+        const int jm = (t + u * T) & (NS - 1);
+        return ldg_c(tw + jm * (L / (NS * R)));
+    }
+    // PRE: seeds of this stage, fetched by the previous stage before its exchange (nullptr: fetch here)
     static __device__ __forceinline__ void run(cplx (&v)[16], cplx *sm, const cplx *__restrict__ tw,
-                                               const int t0, const int q0, const int t1, const int q1, Hook &hook) {
+                                               const int t0, const int q0, const int t1, const int q1, Hook &hook,
+                                               const cplx *pre = nullptr) {
         const int t = STAGE == 0 ? t0 : t1, q = STAGE == 0 ? q0 : q1;
         if constexpr (STAGE > 0) {
             // exchange: previous stage wrote its scattered outputs; gather t + m*T
@@ -419,8 +463,7 @@ struct Stages {
             // LSU<->register datapath, not the FP64 pipe, is the scarce resource of this kernel.
 #pragma unroll
             for (int u = 0; u < NB; u++) {
-                const int jm = (t + u * T) & (NS - 1);
-                const cplx w1 = ldg_c(tw + jm * (L / (NS * R)));
+                const cplx w1 = pre ? pre[u] : load_seed(tw, t, u);
                 twiddle_powers<R, NB>(v, u, w1);
             }
         }
@@ -434,6 +477,15 @@ struct Stages {
             for (int s = 0; s < R; s++) v[u + s * NB] = w[s];
         }
         if constexpr (STAGE + 1 < NSTAGES) {
+            using Next = Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PLANAR, PRESYNC0, Sync, Hook>;
+            // the next stage's seeds depend only on the thread: fetch them now, so that their latency
+            // (an L2 round trip whenever L1 was invalidated by a fence) hides behind the exchange
+            constexpr bool PREFETCH = Next::NB <= 2;
+            cplx wn[PREFETCH ? Next::NB : 1];
+            if constexpr (PREFETCH) {
+#pragma unroll
+                for (int u = 0; u < Next::NB; u++) wn[u] = Next::load_seed(tw, t1, u);
+            }
             if constexpr (STAGE > 0 || PRESYNC0) Sync::sync();   // everyone has gathered before we overwrite
 #pragma unroll
             for (int u = 0; u < NB; u++) {
@@ -443,7 +495,7 @@ struct Stages {
                 for (int s = 0; s < R; s++) sm[smem_phys<LOG2L, PLANAR>(base + s * NS, q)] = v[u + s * NB];
             }
             Sync::sync();
-            Stages<LOG2L, STAGE + 1, LOG2NS + LOG2R, PLANAR, PRESYNC0, Sync, Hook>::run(v, sm, tw, t0, q0, t1, q1, hook);
+            Next::run(v, sm, tw, t0, q0, t1, q1, hook, PREFETCH ? wn : nullptr);
         }
     }
 };
@@ -631,6 +683,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(s0 + m * step, src_hint, pol);
         }
+        hook.loads_issued();
         if (flags & PF_SCALE) {
             const double sc = p.scale;
 #pragma unroll
@@ -659,6 +712,7 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
             for (int m = 0; m < 16; m++) v[m].y = -v[m].y;
         }
     } else {
+        hook.loads_issued();
 #pragma unroll
         for (int m = 0; m < 16; m++) v[m] = make_double2(0.0, 0.0);
     }
@@ -848,8 +902,10 @@ struct FusedParams {
     PassParams a, b;                 // pass A (first executed) and pass B, geometry as launch_pass would set it
     long long items;                 // batch
     int upg, nunits;                 // transforms per unit, units
+    int lead;                        // D: pass A runs D units ahead of pass B; the ring (natural order) has D + 1 slots
     unsigned *done_a, *done_b;       // [nunits] finished-tile counters, zeroed before the launch
     int *error;                      // set to 1 if a wait timed out (never expected)
+    int prefetch;                    // 1: pull each CTA's next pass-A tile into L2 while the current tile runs
 };
 
 __host__ __device__ constexpr unsigned fused_flags_a(int pk) {
@@ -890,9 +946,54 @@ template <int LCOL, int LROW> __device__ __forceinline__ void fold_row_geometry(
     q.d_SA = q.s_SA; q.d_SG = q.s_SG; q.d_i = q.s_i; q.d_q = q.s_q;
 }
 
+// This CTA's tiles of the flat phase list, in order.  With lead D = p.lead the list is
+//      A(0) .. A(D-1) | B(0) A(D) | B(1) A(D+1) | B(2) A(D+2) | ...
+// so that between A(u) and B(u) lie 2 (D - 1) other phases, and between B(u) and the pass that reuses its
+// ring slot (A(u + D + 1), ring of D + 1 slots) lie 2 D - 1.  A unit past the end is an empty phase.
+struct FlatTiles {
+    long long G, items, tfull, base, s, tu;
+    int upg, nunits, nphases, lgtpi, lead, ph, u;
+    bool is_b;
+    __device__ __forceinline__ void load_phase() {
+        if (ph < lead) { is_b = false; u = ph; }
+        else { const int j = ph - lead; is_b = !(j & 1); u = is_b ? (j >> 1) : lead + (j >> 1); }
+        const long long left = items - (long long)u * upg;
+        tu = u < nunits ? ((left < upg ? left : (long long)upg) << lgtpi) : 0;
+    }
+    __device__ __forceinline__ void init(const FusedParams &p, int lgtpi_) {
+        G = (long long)gridDim.x; items = p.items; upg = p.upg; nunits = p.nunits; lead = p.lead; lgtpi = lgtpi_;
+        nphases = p.lead + 2 * p.nunits;
+        tfull = (long long)p.upg << lgtpi_;
+        ph = 0; base = 0; s = (long long)blockIdx.x - G;
+        load_phase();
+    }
+    // advances to the next tile; false when the list is exhausted
+    __device__ __forceinline__ bool next(long long &tile) {
+        s += G;
+        while (s >= base + tu) {
+            base += tu;
+            if (++ph >= nphases) return false;
+            load_phase();
+        }
+        tile = (long long)u * tfull + (s - base);
+        return true;
+    }
+    // ring slot of unit u holds items [slot * upg, ...): what to add to an item index of unit u
+    __device__ __forceinline__ long long ring_delta() const { return ((long long)(u % (lead + 1)) - u) * upg; }
+};
+
+__device__ __forceinline__ void publish_tile_relaxed(unsigned *ctr) {
+#ifdef NAPA_EMULATE
+    *ctr += 1;
+    napa_emul::note_progress();
+#else
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(ctr) : "memory");
+#endif
+}
 __device__ __forceinline__ void publish_tile(unsigned *ctr) {
 #ifdef NAPA_EMULATE
     *ctr += 1;
+    napa_emul::note_progress();
 #else
     // release at gpu scope: the CTA's stores (ordered before this thread by the preceding barrier) come first
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(ctr) : "memory");
@@ -909,6 +1010,38 @@ __device__ __forceinline__ void await_tiles(const unsigned *ctr, const unsigned 
     }
     __syncthreads();
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+#ifndef NAPA_EMULATE
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+// What a fused-kernel CTA does while a tile's loads are in flight: publish the previous tile (the release
+// fence then waits in the shadow of the loads instead of holding up the CTA's next barrier) and pull
+// the source lines of its NEXT pass-A tile from HBM into L2, so that tile's loads pay an L2 round trip.
+// A tile is 2^LGPTS points = NL 128-byte lines: `runs` contiguous runs of `run_lines` lines, `run_stride` elements apart.
+struct FusedHook {
+    unsigned *pending = nullptr;
+    const cplx *pf = nullptr;                // first element of the tile to prefetch (nullptr: nothing)
+    long long pf_run_stride = 0;
+    int pf_lg_run_lines = 0, pf_lines = 0;
+    __device__ __forceinline__ void operator()() const {}
+    // publish now: required before this CTA waits on a counter (its own unpublished tile may be what is missing)
+    __device__ __forceinline__ void flush() {
+        if (threadIdx.x == 0 && pending) publish_tile(pending);
+        pending = nullptr;
+    }
+    __device__ __forceinline__ void loads_issued() {
+        flush();
+        if (pf) {
+            for (int j = (int)threadIdx.x; j < pf_lines; j += (int)blockDim.x)
+                prefetch_l2(pf + (long long)(j >> pf_lg_run_lines) * pf_run_stride + ((j & ((1 << pf_lg_run_lines) - 1)) << 3));
+            pf = nullptr;
+        }
+    }
+};
 
 template <int LA, int LB, int PK, bool WIN>
 __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_fused_kernel(const NAPA_GRID_CONSTANT FusedParams p) {
@@ -930,47 +1063,235 @@ __global__ void __launch_bounds__(plan_threads(LA), plan_min_ctas(LA)) fft_fused
     pa.src_hint = HINT_STREAM; pa.dst_hint = HINT_KEEP; pb.src_hint = HINT_KEEP; pb.dst_hint = HINT_STREAM;
     pa.lgN = LA + LB; pb.lgN = LA + LB;
 
-    const long long G = (long long)gridDim.x, c = (long long)blockIdx.x;
-    const long long tfull = (long long)p.upg << LGTPI;          // tiles per full unit and pass
+    // source lines of a pass-A tile, for the L2 prefetch: runs of contiguous 128-byte lines
+    constexpr int LGPTS = plan_log2pts(LA);
+    constexpr bool A_IS_ROW = PK == 2;
+    constexpr int A_LG_RUN_LINES = A_IS_ROW ? LA - 3 : plan_log2c(LA) - 3;       // a row of 2^LA points / C adjacent columns
+    const bool can_prefetch = p.prefetch && !(pa.flags & (PF_ZIP2 | PF_RIFFT_PRE));
     int known_a = -1, known_b = -1;                               // newest unit whose pass is known to be complete
-    unsigned *pending = nullptr;                                  // counter owed one increment for the tile just stored
-    long long base = 0;                                           // flat slot of the phase's first tile
-    const int nphases = 2 * p.nunits;
-    for (int ph = 0; ph < nphases; ph++) {
-        // phase list = A0 A1 B0 B1 | A2 A3 B2 B3 | ...
-        int u; bool is_b;
-        {
-            const int q4 = ph >> 2, r4 = ph & 3;
-            is_b = r4 >= 2; u = 2 * q4 + (r4 & 1);
-            if (u >= p.nunits) {
-                // an odd unit count: the last block is A(u0) B(u0) with u0 = nunits - 1
-                const int u0 = p.nunits - 1;
-                is_b = ((ph - 4 * (u0 >> 1)) & 1) != 0; u = u0;
+    FusedHook hook;
+    FlatTiles it;
+    it.init(p, LGTPI);
+    long long tile;
+    while (it.next(tile)) {
+        __syncthreads();                             // the previous tile is done with sm and has issued its stores
+        // this CTA's next tile: if it belongs to a pass A, its source lines are prefetched into L2 now
+        if (can_prefetch) {
+            FlatTiles nx = it;
+            long long t2;
+            if (nx.next(t2) && !nx.is_b) {
+                const long long item2 = t2 >> LGTPI; const int r2 = (int)(t2 & ((1 << LGTPI) - 1));
+                hook.pf = pa.src + item2 * pa.src_batch_stride + (A_IS_ROW ? (long long)r2 * pa.s_SA : (long long)r2 * pa.s_SG);
+                hook.pf_run_stride = A_IS_ROW ? pa.s_q : pa.s_i;
+                hook.pf_lg_run_lines = A_LG_RUN_LINES; hook.pf_lines = 1 << (LGPTS - 3);
             }
         }
-        const long long left = p.items - (long long)u * p.upg;
-        const long long tu = (left < p.upg ? left : (long long)p.upg) << LGTPI;
-        long long s = base + ((c - base % G) + G) % G;
-        for (; s < base + tu; s += G) {
-            const long long tile = (long long)u * tfull + (s - base);
-            __syncthreads();                             // the previous tile is done with sm and has issued its stores
-            if (threadIdx.x == 0 && pending) publish_tile(pending);
-            pending = nullptr;
-            const long long ring_delta = RING ? ((long long)(u & 1) - u) * p.upg : 0;
-            if (!is_b) {
-                if (RING && u >= 2 && u - 2 > known_b) { await_tiles(p.done_b + (u - 2), (unsigned)tfull, p.error); known_b = u - 2; }
-                run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, NoHook, ALLOW_A>(pa, tile, sm, 0, ring_delta, pol, nh);
-                pending = p.done_a + u;
-            } else {
-                if (u > known_a) { await_tiles(p.done_a + u, (unsigned)tu, p.error); known_a = u; }
-                run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, NoHook, fused_flags_b(PK)>(pb, tile, sm, ring_delta, 0, pol, nh);
-                pending = RING ? p.done_b + u : nullptr;
-            }
+        const int u = it.u;
+        const long long ring_delta = RING ? it.ring_delta() : 0;
+        if (!it.is_b) {
+            if (RING && u > p.lead && u - p.lead - 1 > known_b) { hook.flush(); await_tiles(p.done_b + (u - p.lead - 1), (unsigned)it.tfull, p.error); known_b = u - p.lead - 1; }
+            run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncAll, false, FusedHook, ALLOW_A>(pa, tile, sm, 0, ring_delta, pol, hook);
+            hook.pending = p.done_a + u;
+        } else {
+            if (u > known_a) { hook.flush(); await_tiles(p.done_a + u, (unsigned)it.tu, p.error); known_a = u; }
+            run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncAll, false, FusedHook, fused_flags_b(PK)>(pb, tile, sm, ring_delta, 0, pol, hook);
+            hook.pending = RING ? p.done_b + u : nullptr;
         }
-        base += tu;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && pending) publish_tile(pending);
+    if (threadIdx.x == 0 && hook.pending) publish_tile(hook.pending);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised variant of the fused kernel (TMA-fed): the same flat phase list and tile counters,
+// but a CTA is `NC` compute threads plus ONE producer warp, and every tile's input is brought into
+// shared memory by the TMA engine while the previous tile is still being computed:
+//   * column tiles (L rows of C adjacent points): one cp.async.bulk.tensor.3d through a tensor map of the
+//     operand ([item][row][2*col] doubles, box = one tile);
+//   * row tiles (C consecutive rows = one contiguous block): one cp.async.bulk.
+// Two buffers per CTA; a buffer holds a tile's staged input and then its exchanges.  Protocol per
+// buffer: full[b] (producer's expect_tx + the copy's bytes) -> compute threads read, compute, store ->
+// every compute thread arrives on done[b] -> the producer publishes the tile (release increment of its
+// unit's counter) and may refill the buffer.  The producer alone touches the inter-CTA counters: it waits
+// for a tile's dependency (all pass-A tiles of its unit in / the ring slot's last reader done) BEFORE
+// issuing its copy, one to two tiles ahead of the compute threads, which therefore never wait on
+// global memory or on another CTA -- only on their own mbarriers.
+// Tiles whose load cannot be staged (PK 2 pass A: a bit-reversed row load goes through the swizzled reorder
+// buffer) are loaded by the compute threads as in fft_fused_kernel; the producer only arms their barrier.
+// ------------------------------------------------------------------------------------------
+struct FusedTmaParams {
+    alignas(64) unsigned long long tmap_a[16];     // CUtensorMap of pass A's source (PK 0 / 1)
+    alignas(64) unsigned long long tmap_b[16];     // CUtensorMap of pass B's source (PK 2)
+    FusedParams f;
+};
+
+__host__ __device__ constexpr bool fused_tma_stage_a(int pk) { return pk != 2; }
+__host__ __device__ constexpr size_t fused_tma_smem_bytes(int la, int lb, int pk) { return 2 * fused_smem_bytes(la, lb, pk) + 64; }
+
+template <int LA, int LB, int PK, bool WIN>
+__global__ void __launch_bounds__(plan_threads(LA) + 32, plan_min_ctas(LA) > 1 ? plan_min_ctas(LA) - 1 : 1)
+fft_fused_tma_kernel(const NAPA_GRID_CONSTANT FusedTmaParams P) {
+    static_assert(plan_threads(LA) == plan_threads(LB), "both passes of a fused pair use the same tile shape");
+    const FusedParams &p = P.f;
+    constexpr int NC = plan_threads(LA);
+    constexpr int KA = fused_kind_a(PK), KB = fused_kind_b(PK);
+    constexpr int LGPTS = plan_log2pts(LA);
+    constexpr int LGTPI = LA + LB - LGPTS;
+    constexpr bool RING = PK == 0;
+    constexpr bool STA = fused_tma_stage_a(PK);
+    constexpr unsigned ALLOW_A = WIN ? fused_flags_a(PK) : (fused_flags_a(PK) & ~FUSED_WINDOW_FLAGS);
+    constexpr size_t BUF = fused_smem_bytes(LA, LB, PK) / sizeof(cplx);
+    constexpr unsigned TILE_BYTES = (unsigned)(sizeof(cplx) << LGPTS);
+    NAPA_DYN_SMEM(cplx, sm);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(sm + 2 * BUF), *done = full + 2;
+    const L2Policies pol = make_policies();
+    PassParams pa = p.a, pb = p.b;
+    if (PK == 2) { fold_row_geometry<LB, LA>(pa); fold_col_geometry<LB, LA>(pb); }
+    else         { fold_col_geometry<LA, LB>(pa); fold_row_geometry<LA, LB>(pb); }
+    if (PK == 0) { pb.d_SA = 1 << plan_log2c(LB); pb.d_SG = 0; pb.d_i = 1LL << LA; pb.d_q = 1; }
+    pa.flags = (p.a.flags & ~fused_fixed_a(PK) & ALLOW_A) | fused_fixed_a(PK);
+    pb.flags = (p.b.flags & ~fused_fixed_b(PK) & fused_flags_b(PK)) | fused_fixed_b(PK);
+    pa.src_hint = HINT_STREAM; pa.dst_hint = HINT_KEEP; pb.src_hint = HINT_KEEP; pb.dst_hint = HINT_STREAM;
+    pa.lgN = LA + LB; pb.lgN = LA + LB;
+
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1); mbar_init(full + 1, 1); mbar_init(done, NC); mbar_init(done + 1, NC);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    FlatTiles it;
+    it.init(p, LGTPI);
+    long long tile;
+
+    if ((int)threadIdx.x >= NC) {
+        // ---------------- producer: one elected thread ----------------
+        if ((int)threadIdx.x != NC) return;
+        unsigned *owed[2] = { nullptr, nullptr };        // counter the tile in buffer b will be published on
+        unsigned *unpublished[2] = { nullptr, nullptr }; // ... and, once the tile is complete, until it has been
+        bool busy[2] = { false, false };                 // buffer b holds a tile whose completion has not been seen
+        unsigned par_done[2] = { 0, 0 };
+        int known_a = -1, known_b = -1;
+        // completion of the tile in buffer b (its compute threads have issued their stores and left the buffer)
+        auto complete = [&](const int b, const bool blocking) {
+            if (!busy[b]) return;
+            if (blocking) mbar_wait(done + b, par_done[b]);
+            else if (!mbar_test(done + b, par_done[b])) return;
+            par_done[b] ^= 1u; busy[b] = false;
+            unpublished[b] = owed[b]; owed[b] = nullptr;
+        };
+        // relaxed increment of the counters of every complete tile, older buffer first; the caller has fenced
+        auto publish_fenced = [&](const int older) {
+            if (unpublished[older]) { publish_tile_relaxed(unpublished[older]); unpublished[older] = nullptr; }
+            if (unpublished[older ^ 1]) { publish_tile_relaxed(unpublished[older ^ 1]); unpublished[older ^ 1] = nullptr; }
+        };
+        // the dependency of a tile: the counter that must reach `need` before its copy may be issued
+        auto dependency = [&](const FlatTiles &t, const unsigned *&dep, unsigned &need) {
+            dep = nullptr; need = 0;
+            if (t.is_b) { if (t.u > known_a) { dep = p.done_a + t.u; need = (unsigned)t.tu; } }
+            else if (RING && t.u > p.lead && t.u - p.lead - 1 > known_b) { dep = p.done_b + (t.u - p.lead - 1); need = (unsigned)t.tfull; }
+        };
+        auto dependency_met = [&](const FlatTiles &t) { if (t.is_b) known_a = t.u; else known_b = t.u - p.lead - 1; };
+        // One fence.acq_rel.gpu per tile does double duty.  RELEASE: the finished tiles' stores (ordered before this
+        // thread by done[b]) come before the relaxed increments that publish them.  ACQUIRE: the relaxed read of the
+        // NEXT tile's dependency counter, issued just before the fence, comes before that tile's copy.  The fence's
+        // latency (the CTA's stores draining to L2) is paid after the current tile's copy has been issued and
+        // overlaps the counter read.
+        bool have_next = it.next(tile);
+        for (int k = 0; have_next; k++) {
+            const int b = k & 1;
+            // 1. dependency of tile k: normally established by the previous iteration's fence; else wait here, and
+            //    keep publishing finished tiles meanwhile (they may be exactly what the rest of the grid waits for)
+            const unsigned *dep; unsigned need;
+            dependency(it, dep, need);
+            if (dep) {
+                unsigned spins = 0;
+                while (ld_relaxed_u32(dep) < need) {
+                    complete(b, false); complete(b ^ 1, false);
+                    if (unpublished[0] || unpublished[1]) { fence_acq_rel_gpu(); publish_fenced(b); }
+                    napa_nanosleep(32);
+                    if (++spins > (1u << 26)) { *p.error = 1; break; }
+                }
+                fence_acq_rel_gpu();
+                dependency_met(it);
+                // the other CTAs' generic-proxy stores, acquired above, come before this thread's TMA reads of them
+                fence_proxy_async();
+            }
+            // 2. the buffer: tile k - 2 must have left it (the mbarrier orders its compute threads' accesses first)
+            complete(b, true);
+            // 3. issue the copy at once; 4. only then pay for the release fences of the finished tiles
+            const long long item = tile >> LGTPI; const int r = (int)(tile & ((1 << LGTPI) - 1));
+            const long long ring_delta = RING ? it.ring_delta() : 0;
+            cplx *buf = sm + (size_t)b * BUF;
+            if (!it.is_b) {
+                if (STA) {
+                    // column tile of pass A: columns [r*C, r*C + C) of item `item` of the source
+                    mbar_expect_tx(full + b, TILE_BYTES);
+#ifdef NAPA_EMULATE
+                    const cplx *g = pa.src + item * pa.src_batch_stride + (long long)r * pa.s_SG;
+                    for (int i = 0; i < (1 << LA); i++) bulk_g2s(buf + ((size_t)i << plan_log2c(LA)), g + (long long)i * pa.s_i, (unsigned)(sizeof(cplx) << plan_log2c(LA)), full + b, 0, pol);
+                    mbar_emul_complete(full + b);
+#else
+                    tma_tile_g2s(buf, P.tmap_a, 2 * (r << plan_log2c(LA)), 0, (int)item, full + b, HINT_STREAM, pol);
+#endif
+                } else {
+                    mbar_arrive(full + b);                // not staged: the compute threads load it themselves
+                }
+                owed[b] = p.done_a + it.u;
+            } else {
+                mbar_expect_tx(full + b, TILE_BYTES);
+                if (PK == 2) {
+                    // column tile of pass B, in place on dst
+#ifdef NAPA_EMULATE
+                    const cplx *g = pb.src + item * pb.src_batch_stride + (long long)r * pb.s_SG;
+                    for (int i = 0; i < (1 << LB); i++) bulk_g2s(buf + ((size_t)i << plan_log2c(LB)), g + (long long)i * pb.s_i, (unsigned)(sizeof(cplx) << plan_log2c(LB)), full + b, 0, pol);
+#else
+                    tma_tile_g2s(buf, P.tmap_b, 2 * (r << plan_log2c(LB)), 0, (int)item, full + b, HINT_KEEP, pol);
+#endif
+                } else {
+                    // row tile: C consecutive rows of the intermediate = one contiguous block
+                    bulk_g2s(buf, pb.src + (item + ring_delta) * pb.src_batch_stride + (long long)r * pb.s_SA, TILE_BYTES, full + b, HINT_KEEP, pol);
+                }
+                mbar_emul_complete(full + b);
+                owed[b] = RING ? p.done_b + it.u : nullptr;
+            }
+            busy[b] = true;
+            // 4. next tile's dependency counter (relaxed, not waited for) + the fence + the publications
+            have_next = it.next(tile);
+            const unsigned *dep2 = nullptr; unsigned need2 = 0, seen2 = 0;
+            if (have_next) { dependency(it, dep2, need2); if (dep2) seen2 = ld_relaxed_u32(dep2); }
+            if (unpublished[0] || unpublished[1] || dep2) {
+                fence_acq_rel_gpu();
+                publish_fenced(b);
+                if (dep2 && seen2 >= need2) { dependency_met(it); fence_proxy_async(); }
+            }
+        }
+        complete(0, true); complete(1, true);
+        fence_acq_rel_gpu(); publish_fenced(0);
+        return;
+    }
+
+    // ---------------- compute threads ----------------
+    NoHook nh;
+    unsigned par_full[2] = { 0, 0 };
+    for (int k = 0; it.next(tile); k++) {
+        const int b = k & 1;
+        cplx *buf = sm + (size_t)b * BUF;
+        const long long ring_delta = RING ? it.ring_delta() : 0;
+        if (!it.is_b) {
+            if (STA) {
+                run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncCompute<NC>, true, NoHook, ALLOW_A, true, true>(
+                    pa, tile, buf, 0, ring_delta, pol, nh, full + b, par_full[b]);
+            } else {
+                mbar_wait(full + b, par_full[b]);
+                run_tile<LA, false, kind_lm(LA, KA), kind_sm(LA, KA), SyncCompute<NC>, true, NoHook, ALLOW_A>(pa, tile, buf, 0, ring_delta, pol, nh);
+            }
+        } else {
+            run_tile<LB, true, kind_lm(LB, KB), kind_sm(LB, KB), SyncCompute<NC>, true, NoHook, fused_flags_b(PK), true, true>(
+                pb, tile, buf, ring_delta, 0, pol, nh, full + b, par_full[b]);
+        }
+        par_full[b] ^= 1u;
+        mbar_arrive(done + b);        // stores issued, buffer free (the producer fences the proxies before it refills it)
+    }
 }
 
 // ------------------------------------------------------------------------------------------

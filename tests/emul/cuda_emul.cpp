@@ -37,16 +37,24 @@ static void yield_fiber() {
     swapcontext(&fibers[current].ctx, &sched_ctx);
 }
 
+// named barriers are per CTA: in cooperative mode every CTA has its own set (coop_named below)
+static unsigned *named_arrived(int id);
+static unsigned long long *named_gen(int id);
+static void yield_current();
+
+void note_progress() { progress++; }
+
 void bar_arrive(int id, unsigned count) {
     progress++;
-    if (++bar_arrived[id] >= count) { bar_arrived[id] = 0; bar_gen[id]++; }
+    if (++*named_arrived(id) >= count) { *named_arrived(id) = 0; ++*named_gen(id); }
 }
 
 void bar_sync(int id, unsigned count) {
     progress++;
-    if (++bar_arrived[id] >= count) { bar_arrived[id] = 0; bar_gen[id]++; return; }
-    const unsigned long long g = bar_gen[id];
-    while (bar_gen[id] == g) yield_fiber();
+    if (++*named_arrived(id) >= count) { *named_arrived(id) = 0; ++*named_gen(id); return; }
+    unsigned long long *gen = named_gen(id);
+    const unsigned long long g = *gen;
+    while (*gen == g) yield_current();
 }
 
 void syncthreads();
@@ -105,7 +113,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
 // dynamic shared memory is per CTA and swapped in with the fiber, and a fiber that spins on another
 // CTA's progress gives way through yield_spin().
 namespace {
-struct CoopBlock { unsigned arrived; unsigned long long gen; unsigned char *smem; };
+struct CoopBlock { unsigned arrived; unsigned long long gen; unsigned char *smem; unsigned n_arrived[16]; unsigned long long n_gen[16]; };
 std::vector<CoopBlock> coop_blocks;
 std::vector<Fiber> coop_fibers;
 bool coop_mode = false;
@@ -125,6 +133,16 @@ void coop_yield() {
 void yield_spin() {
     if (coop_mode) coop_yield();
 }
+static void yield_current() {
+    if (coop_mode) coop_yield(); else yield_fiber();
+}
+void yield_any() { yield_current(); }
+static unsigned *named_arrived(int id) {
+    return coop_mode ? &coop_blocks[(size_t)coop_current / coop_threads].n_arrived[id] : &bar_arrived[id];
+}
+static unsigned long long *named_gen(int id) {
+    return coop_mode ? &coop_blocks[(size_t)coop_current / coop_threads].n_gen[id] : &bar_gen[id];
+}
 
 void syncthreads() {
     if (!coop_mode) { bar_sync(0, blockDim_.x * blockDim_.y * blockDim_.z); return; }
@@ -143,7 +161,7 @@ void launch_cooperative(dim3 grid, dim3 block, size_t smem, const std::function<
         coop_fibers.resize(total);
         for (size_t i = old; i < total; i++) coop_fibers[i].stack = (unsigned char *)malloc(kStack);
     }
-    coop_blocks.assign(nblocks, CoopBlock{0, 0, nullptr});
+    coop_blocks.assign(nblocks, CoopBlock{});
     for (unsigned b = 0; b < nblocks; b++) {
         void *sm = nullptr;
         if (posix_memalign(&sm, 128, smem ? smem : 16)) abort();

@@ -42,6 +42,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
 // every CTA alive at once (round-robin over all fibers of the grid): kernels whose CTAs wait on each other
 void launch_cooperative(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 void yield_spin();                           // called from a spin-wait on another CTA's progress
+void yield_any();                            // spin-wait on another THREAD's progress (same CTA or not), any launch mode
+void note_progress();                        // a waited-for event happened (mbarrier arrival, counter increment)
 void syncthreads();
 void bar_sync(int id, unsigned count);      // named barrier (bar.sync id, count)
 void bar_arrive(int id, unsigned count);    // bar.arrive id, count

@@ -1,4 +1,4 @@
-"""Runs two-digit transforms (2^14 .. 2^20: the fused single-launch kernel unless NAPAFFT_FUSED=0; the
+"""Runs two-digit transforms (2^14 .. 2^20: through the fused single-launch kernels when NAPAFFT_FUSED=1; the
 tuning variables NAPAFFT_FUSED* are read at library init, hence a separate process).
 argv[1]: "emul" (CPU emulation build) or "gpu"."""
 import os
@@ -34,7 +34,8 @@ for lg in sizes:
         assert S.nre(back, x) <= S.tol(n)
     # the real wrappers ride on the same plans (zip / rifft pre-twiddle fused into the first pass)
     S.check_2rfft(napa, n)
-    S.check_real(napa, 2 * n, "sqrt")
+    if "NAPAFFT_MAX_SCRATCH_KB" not in os.environ:     # (rifft has no in-place fallback: it reports NAPA_E_UNSUPPORTED)
+        S.check_real(napa, 2 * n, "sqrt")
 if sys.argv[1] != "emul":
     # many units per launch: ring-slot reuse, ragged last unit, every CTA crossing many phases
     for lg, batch in ((14, 1500), (16, 333), (18, 70)):

@@ -118,14 +118,15 @@ def test_many_tiles_single_pass(napa, n, batch):
 
 
 def test_fused_kernel_schedules():
-    """the fused single-launch kernel (default for 2^14 .. 2^20) under several schedules: the emulator keeps every CTA
-    of a cooperative launch alive (tests/emul/cuda_emul.cpp: launch_cooperative), so the tile counters, the waits on
-    them, ring-slot reuse, ragged last units and odd unit counts all really run; and the same cases with the fused
-    plans switched off (one launch per digit pass)"""
+    """the fused single-launch kernels (opt-in, NAPAFFT_FUSED=1; direct-load and TMA-fed warp-specialised variants)
+    under several schedules: the emulator keeps every CTA of a cooperative launch alive (tests/emul/cuda_emul.cpp:
+    launch_cooperative) and emulates mbarriers, so the tile counters, the waits on them, the producer / compute-thread
+    hand-off, ring-slot reuse, ragged last units and odd unit counts all really run; the default plans (one launch per
+    digit pass) are covered by every other test of this file"""
     import subprocess
-    for extra in ({}, {"NAPAFFT_FUSED_UPG": "1", "NAPAFFT_FUSED_GRID": "2"}, {"NAPAFFT_FUSED_UPG": "3", "NAPAFFT_FUSED_GRID": "5"},
-                  {"NAPAFFT_FUSED": "0"}):
-        env = dict(os.environ, **extra)
+    for extra in ({}, {"NAPAFFT_FUSED_TMA": "1"}, {"NAPAFFT_FUSED_UPG": "1", "NAPAFFT_FUSED_GRID": "2", "NAPAFFT_FUSED_LEAD": "1"},
+                  {"NAPAFFT_FUSED_TMA": "1", "NAPAFFT_FUSED_UPG": "3", "NAPAFFT_FUSED_GRID": "5", "NAPAFFT_FUSED_LEAD": "3"}):
+        env = dict(os.environ, NAPAFFT_FUSED="1", **extra)
         out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_probe.py"), "emul"],
                              env=env, capture_output=True, text=True, timeout=1200)
         assert out.returncode == 0 and "fused ok" in out.stdout, str(extra) + out.stdout[-2000:] + out.stderr[-2000:]

@@ -189,12 +189,13 @@ def test_distributed_building_blocks_single_rank(napa, lgN):
 
 
 def test_fused_kernel_schedules_gpu():
-    """fused single-launch kernel (default for 2^14 .. 2^20): automatic unit / grid shape, one transform per unit on a
-    small grid (every CTA crosses many phases and really waits on the counters), wide units, and the same cases
-    with the fused plans off (one launch per digit pass)"""
+    """fused single-launch kernels (opt-in, NAPAFFT_FUSED=1): automatic unit / grid shape for the direct-load and the
+    TMA-fed variant, one transform per unit on a small grid (every CTA crosses many phases and really waits on the
+    counters), wide units with a long lead"""
     import subprocess
-    for extra in ({}, {"NAPAFFT_FUSED_UPG": "1", "NAPAFFT_FUSED_GRID": "37"}, {"NAPAFFT_FUSED_UPG": "5"}, {"NAPAFFT_FUSED": "0"}):
-        env = dict(os.environ, **extra)
+    for extra in ({}, {"NAPAFFT_FUSED_TMA": "1"}, {"NAPAFFT_FUSED_UPG": "1", "NAPAFFT_FUSED_GRID": "37", "NAPAFFT_FUSED_LEAD": "1"},
+                  {"NAPAFFT_FUSED_TMA": "1", "NAPAFFT_FUSED_UPG": "5", "NAPAFFT_FUSED_LEAD": "3"}):
+        env = dict(os.environ, NAPAFFT_FUSED="1", **extra)
         out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_probe.py"), "gpu"],
                              env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "fused ok" in out.stdout, str(extra) + out.stdout[-2000:] + out.stderr[-2000:]
