@@ -61,21 +61,27 @@ static inline int ilog2(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++;
 struct BigTw { cplx *lo = nullptr, *hi = nullptr; int shift = 0; };
 struct PairTable { unsigned *dev = nullptr; int count = 0; };
 
+// Staging resources of ONE calling host thread (host-pointer entry points): two streams, two device buffers and
+// two page-locked buffers, so that concurrent callers on distinct vectors (README:811-814 of the reference allows
+// them) each run their own H2D -> kernels -> D2H pipeline and only meet at the short, mutex-protected launch step.
+struct Staging {
+    cudaStream_t stream[2] = {};
+    cudaEvent_t done[2] = {};
+    void *pinned[2] = {}; size_t pinned_bytes = 0;
+    void *dbuf[2] = {}; size_t dbuf_bytes = 0;
+    void *dwin = nullptr; size_t dwin_bytes = 0;
+};
+
 struct State {
-    std::mutex mu;
-    bool inited = false;
+    std::mutex mu;                                   // caches, tables, per-stream scratch, kernel attributes, launches
+    std::atomic<bool> inited{false};
+    std::vector<Staging *> stagings;                 // every thread's staging block (released by napafft_shutdown)
     int device = -1;
     cplx *stage_tw[14] = {};
     std::map<int, BigTw> big;                        // by log2 M
     std::map<std::pair<size_t, int>, cplx *> r2tw;   // (n, dir) -> n/2 entries (reference recurrence)
     std::map<int, PairTable> pairs;                  // bit-reversal tile pairs by width
     std::map<cudaStream_t, std::pair<cplx *, size_t>> scratch;   // natural-order intermediate, one per stream
-    // staging for host-pointer calls
-    cudaStream_t stream[2] = {};
-    cudaEvent_t done[2] = {};
-    void *pinned[2] = {}; size_t pinned_bytes = 0;
-    void *dbuf[2] = {}; size_t dbuf_bytes = 0;
-    void *dwin = nullptr; size_t dwin_bytes = 0;
     size_t chunk_bytes = (size_t)2 << 30; // bytes of transforms per launch of the multi-pass path = natural-order scratch size (2 GiB: +0.7 % over 1 GiB on C2, 4 GiB +0.8 %)
     std::map<cudaStream_t, std::pair<cplx *, size_t>> oa_buf;    // chunk matrix + energies of the overlap-add filter, one per stream
     size_t zero_copy_bytes = 128 << 10;   // host-pointer jobs up to this size run on mapped page-locked memory, no copies
@@ -92,10 +98,28 @@ struct State {
     int *h_error = nullptr, *d_error = nullptr;                             // mapped error flag
 };
 static State G;
+static thread_local Staging *tl_staging = nullptr;
+static Staging &staging() {
+    if (!tl_staging) {
+        tl_staging = new Staging();
+        std::lock_guard<std::mutex> lk(G.mu);
+        G.stagings.push_back(tl_staging);
+    }
+    return *tl_staging;
+}
+// every exported function: library bound to a device, and THIS thread's current device is that device
+static int napafft_enter();
+#define LOCKED(expr) [&]() -> int { std::lock_guard<std::mutex> lk_(G.mu); return (expr); }()
 
 static int ensure_init() {
-    if (G.inited) return NAPA_OK;
+    if (G.inited.load()) return NAPA_OK;
     return napafft_init(-1);
+}
+static int napafft_enter() {
+    OK(ensure_init());
+    // the binding is per process, CUDA's current device is per thread: a caller's worker thread starts on device 0
+    CU(cudaSetDevice(G.device));
+    return NAPA_OK;
 }
 
 // W_M^e = exp(-2 pi i e / M), evaluated in long double and rounded once
@@ -1001,30 +1025,32 @@ static int check_c2c_args(const void *src, const void *dst, size_t n, size_t bat
 // host staging
 // ------------------------------------------------------------------------------------------
 static int ensure_staging(size_t chunk_bytes_needed) {
-    if (!G.stream[0]) {
+    Staging &S = staging();
+    if (!S.stream[0]) {
         for (int i = 0; i < 2; i++) {
-            CU(cudaStreamCreateWithFlags(&G.stream[i], cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&G.done[i], cudaEventDisableTiming));
+            CU(cudaStreamCreateWithFlags(&S.stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&S.done[i], cudaEventDisableTiming));
         }
     }
-    if (G.dbuf_bytes < chunk_bytes_needed) {
+    if (S.dbuf_bytes < chunk_bytes_needed) {
         CU(cudaDeviceSynchronize());
         for (int i = 0; i < 2; i++) {
-            if (G.dbuf[i]) CU(cudaFree(G.dbuf[i]));
-            CU(cudaMalloc(&G.dbuf[i], chunk_bytes_needed));
+            if (S.dbuf[i]) CU(cudaFree(S.dbuf[i]));
+            CU(cudaMalloc(&S.dbuf[i], chunk_bytes_needed));
         }
-        G.dbuf_bytes = chunk_bytes_needed;
+        S.dbuf_bytes = chunk_bytes_needed;
     }
     return NAPA_OK;
 }
 static int ensure_pinned(size_t bytes) {
-    if (G.pinned_bytes >= bytes) return NAPA_OK;
+    Staging &S = staging();
+    if (S.pinned_bytes >= bytes) return NAPA_OK;
     CU(cudaDeviceSynchronize());
     for (int i = 0; i < 2; i++) {
-        if (G.pinned[i]) CU(cudaFreeHost(G.pinned[i]));
-        CU(cudaHostAlloc(&G.pinned[i], bytes, cudaHostAllocDefault));
+        if (S.pinned[i]) CU(cudaFreeHost(S.pinned[i]));
+        CU(cudaHostAlloc(&S.pinned[i], bytes, cudaHostAllocDefault));
     }
-    G.pinned_bytes = bytes;
+    S.pinned_bytes = bytes;
     return NAPA_OK;
 }
 static bool is_pinned(const void *p) {
@@ -1033,18 +1059,19 @@ static bool is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 static int upload_window(const void *window, int wtype, size_t count, const void **dev) {
+    Staging &S = staging();
     *dev = nullptr;
     if (!wtype) return NAPA_OK;
     size_t bytes = count * (wtype == NAPA_WINDOW_REAL ? 8 : 16);
-    if (G.dwin_bytes < bytes) {
+    if (S.dwin_bytes < bytes) {
         CU(cudaDeviceSynchronize());
-        if (G.dwin) CU(cudaFree(G.dwin));
-        CU(cudaMalloc(&G.dwin, bytes));
-        G.dwin_bytes = bytes;
+        if (S.dwin) CU(cudaFree(S.dwin));
+        CU(cudaMalloc(&S.dwin, bytes));
+        S.dwin_bytes = bytes;
     }
-    CU(cudaMemcpyAsync(G.dwin, window, bytes, cudaMemcpyHostToDevice, G.stream[0]));
-    CU(cudaStreamSynchronize(G.stream[0]));
-    *dev = G.dwin;
+    CU(cudaMemcpyAsync(S.dwin, window, bytes, cudaMemcpyHostToDevice, S.stream[0]));
+    CU(cudaStreamSynchronize(S.stream[0]));
+    *dev = S.dwin;
     return NAPA_OK;
 }
 
@@ -1060,6 +1087,7 @@ struct HostJob {
 };
 template <typename Body>
 static int run_host_job(const HostJob &j, Body body) {
+    Staging &S = staging();
     const size_t in_total = j.in_item_bytes * (j.src2 ? 2 : 1);
     const size_t per_item = j.inplace ? std::max(in_total, j.out_item_bytes) : in_total + j.out_item_bytes;
     size_t target = (size_t)256 << 20;                                    // device bytes per chunk
@@ -1072,13 +1100,13 @@ static int run_host_job(const HostJob &j, Body body) {
         OK(ensure_staging(0));
         const size_t in_span = (small_in + 255) & ~(size_t)255;
         OK(ensure_pinned(j.inplace ? std::max(in_span, small_out) : in_span + small_out));
-        char *hin = (char *)G.pinned[0], *hout = j.inplace ? hin : hin + in_span;
+        char *hin = (char *)S.pinned[0], *hout = j.inplace ? hin : hin + in_span;
         for (int which = 0; which < (j.src2 ? 2 : 1); which++) {
             const char *hs = which ? j.src2 : j.src;
             char *ph = hin + (which ? j.batch * j.in_item_bytes : 0);
             for (size_t i = 0; i < j.batch; i++) memcpy(ph + i * j.in_item_bytes, hs + i * j.in_pitch, j.in_item_bytes);
         }
-        cudaStream_t st = G.stream[0];
+        cudaStream_t st = S.stream[0];
         OK(body(hin, hout, j.batch, 0, st));
         CU(cudaStreamSynchronize(st));
         for (size_t i = 0; i < j.batch; i++) memcpy(j.dst + i * j.out_pitch, hout + i * j.out_item_bytes, j.out_item_bytes);
@@ -1092,9 +1120,9 @@ static int run_host_job(const HostJob &j, Body body) {
     size_t pending_out[2] = { 0, 0 }, pending_b0[2] = { 0, 0 };
     auto drain = [&](int slot) -> int {
         if (!pending_out[slot]) return NAPA_OK;
-        CU(cudaEventSynchronize(G.done[slot]));
+        CU(cudaEventSynchronize(S.done[slot]));
         if (!dst_pinned) {
-            const char *ph = (const char *)G.pinned[slot];
+            const char *ph = (const char *)S.pinned[slot];
             for (size_t i = 0; i < pending_out[slot]; i++)
                 memcpy(j.dst + (pending_b0[slot] + i) * j.out_pitch, ph + i * j.out_item_bytes, j.out_item_bytes);
         }
@@ -1105,8 +1133,8 @@ static int run_host_job(const HostJob &j, Body body) {
     for (size_t b0 = 0; b0 < j.batch; b0 += items, slot ^= 1) {
         const size_t nb = std::min(items, j.batch - b0);
         OK(drain(slot));
-        cudaStream_t st = G.stream[slot];
-        char *dev_in = (char *)G.dbuf[slot];
+        cudaStream_t st = S.stream[slot];
+        char *dev_in = (char *)S.dbuf[slot];
         char *dev_out = j.inplace ? dev_in : dev_in + ((nb * in_total + 255) & ~(size_t)255);    // keep the output 256-byte aligned
         for (int which = 0; which < (j.src2 ? 2 : 1); which++) {
             const char *hs = which ? j.src2 : j.src;
@@ -1115,7 +1143,7 @@ static int run_host_job(const HostJob &j, Body body) {
                 CU(cudaMemcpy2DAsync(dd, j.in_item_bytes, hs + b0 * j.in_pitch, j.in_pitch, j.in_item_bytes, nb,
                                      cudaMemcpyHostToDevice, st));
             } else {
-                char *ph = (char *)G.pinned[slot] + (which ? nb * j.in_item_bytes : 0);
+                char *ph = (char *)S.pinned[slot] + (which ? nb * j.in_item_bytes : 0);
                 for (size_t i = 0; i < nb; i++) memcpy(ph + i * j.in_item_bytes, hs + (b0 + i) * j.in_pitch, j.in_item_bytes);
                 CU(cudaMemcpyAsync(dd, ph, nb * j.in_item_bytes, cudaMemcpyHostToDevice, st));
             }
@@ -1125,9 +1153,9 @@ static int run_host_job(const HostJob &j, Body body) {
             CU(cudaMemcpy2DAsync(j.dst + b0 * j.out_pitch, j.out_pitch, dev_out, j.out_item_bytes, j.out_item_bytes, nb,
                                  cudaMemcpyDeviceToHost, st));
         } else {
-            CU(cudaMemcpyAsync(G.pinned[slot], dev_out, nb * j.out_item_bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(S.pinned[slot], dev_out, nb * j.out_item_bytes, cudaMemcpyDeviceToHost, st));
         }
-        CU(cudaEventRecord(G.done[slot], st));
+        CU(cudaEventRecord(S.done[slot], st));
         pending_out[slot] = nb; pending_b0[slot] = b0;
     }
     OK(drain(0));
@@ -1196,15 +1224,16 @@ NAPA_API int napafft_shutdown(void) {
     for (auto &kv : G.counters) cudaFree(kv.second.first);
     G.counters.clear();
     if (G.h_error) { cudaFreeHost(G.h_error); G.h_error = nullptr; G.d_error = nullptr; }
-    for (int i = 0; i < 2; i++) {
-        if (G.dbuf[i]) cudaFree(G.dbuf[i]);
-        if (G.pinned[i]) cudaFreeHost(G.pinned[i]);
-        if (G.stream[i]) cudaStreamDestroy(G.stream[i]);
-        if (G.done[i]) cudaEventDestroy(G.done[i]);
-        G.dbuf[i] = G.pinned[i] = nullptr; G.stream[i] = nullptr; G.done[i] = nullptr;
+    for (Staging *S : G.stagings) {
+        for (int i = 0; i < 2; i++) {
+            if (S->dbuf[i]) cudaFree(S->dbuf[i]);
+            if (S->pinned[i]) cudaFreeHost(S->pinned[i]);
+            if (S->stream[i]) cudaStreamDestroy(S->stream[i]);
+            if (S->done[i]) cudaEventDestroy(S->done[i]);
+        }
+        if (S->dwin) cudaFree(S->dwin);
+        *S = Staging();                              // the owning thread re-creates its resources on its next call
     }
-    if (G.dwin) cudaFree(G.dwin);
-    G.dwin = nullptr; G.dwin_bytes = G.dbuf_bytes = G.pinned_bytes = 0;
     G.inited = false;
     return NAPA_OK;
 }
@@ -1223,7 +1252,9 @@ NAPA_API int napafft_c2c_dev(const void *src, void *dst, size_t n, size_t batch,
                              int in_order, const void *window, int window_type, int window_per_batch, void *stream) {
     OK(check_c2c_args(src, dst, n, batch, stride, dir, scale, window, window_type));
     if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(NAPA_E_UNSUPPORTED, "device pointers must be 16-byte aligned");
-    OK(ensure_init());
+    if (window_type == NAPA_WINDOW_COMPLEX && ((uintptr_t)window & 15)) return fail(NAPA_E_UNSUPPORTED, "a complex window must be 16-byte aligned");
+    if (window_type == NAPA_WINDOW_REAL && ((uintptr_t)window & 7)) return fail(NAPA_E_UNSUPPORTED, "a real window must be 8-byte aligned");
+    OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
     C2COpts o{};
     o.dir = dir; o.in_order = in_order; o.scale = scale_factor(n, dir, scale);
@@ -1236,7 +1267,7 @@ NAPA_API int napafft_bit_reverse_dev(const void *src, void *dst, size_t n, size_
     if (!pow2(n)) return fail(NAPA_E_NOT_POW2, "size %zu is not a power of two", n);
     if (elt != NAPA_ELT_COMPLEX && elt != NAPA_ELT_REAL) return fail(NAPA_E_BAD_ENUM, "element type %d", elt);
     if (batch > 1 && stride < n) return fail(NAPA_E_SHORT_BUFFER, "stride %zu shorter than n %zu", stride, n);
-    OK(ensure_init());
+    OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
     return exec_bitrev(src, dst, n, batch, stride, stride, elt, (cudaStream_t)stream);
 }
@@ -1252,29 +1283,33 @@ static int check_real_args(const void *a, const void *b, size_t n, int scale) {
 NAPA_API int napafft_rfft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream) {
     OK(check_real_args(src, dst, n, scale));
     if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(NAPA_E_UNSUPPORTED, "device pointers must be 16-byte aligned");
-    OK(ensure_init());
+    OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
     return exec_rfft((const double *)src, (cplx *)dst, n, batch, scale, (cudaStream_t)stream);
 }
 NAPA_API int napafft_rifft_dev(const void *src, void *dst, size_t n, size_t batch, int scale, void *stream) {
     OK(check_real_args(src, dst, n, scale));
     if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(NAPA_E_UNSUPPORTED, "device pointers must be 16-byte aligned");
-    OK(ensure_init());
+    // item b writes dst[b*n/2 ..] (complex view) while other CTAs still read that region of src: no in-place batches
+    if ((const void *)src == (const void *)dst && batch > 1) return fail(NAPA_E_UNSUPPORTED, "napafft_rifft_dev cannot run a batch in place (src == dst)");
+    OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
     return exec_rifft((const cplx *)src, (double *)dst, n, batch, scale, (cudaStream_t)stream);
 }
 NAPA_API int napafft_2rfft_dev(const void *v1, const void *v2, void *dst, size_t n, size_t batch, int scale, void *stream) {
     OK(check_real_args(v1, dst, n, scale));
     if (!v2) return fail(NAPA_E_NULL, "v2 must not be NULL");
-    OK(ensure_init());
+    if ((((uintptr_t)v1 | (uintptr_t)v2) & 7) || ((uintptr_t)dst & 15)) return fail(NAPA_E_UNSUPPORTED, "v1 / v2 must be 8-byte and dst 16-byte aligned");
+    OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
     return exec_2rfft((const double *)v1, (const double *)v2, (cplx *)dst, n, batch, scale, (cudaStream_t)stream);
 }
 NAPA_API int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, size_t h_stride, void *stream) {
     if (!a || !h) return fail(NAPA_E_NULL, "a/h must not be NULL");
-    OK(ensure_init());
+    OK(napafft_enter());
     const long long total = (long long)n * (long long)batch;
     if (total == 0) return NAPA_OK;
+    std::lock_guard<std::mutex> lk(G.mu);
     NAPA_LAUNCH(napa::cmul_pointwise_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, (cplx *)a,
                 (const cplx *)h, (long long)n, (long long)batch, (long long)h_stride);
     g_launches++;
@@ -1291,7 +1326,7 @@ static int check_filter_args(const void *vec, const void *filter_rev, const void
 NAPA_API int napafft_filter_chunks_dev(const void *vector, size_t len, const void *filter_rev, const void *window, size_t chunk,
                                        void *dst, void *stream) {
     OK(check_filter_args(vector, filter_rev, window, chunk, dst));
-    OK(ensure_init());
+    OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
     return exec_filter_chunks((const double *)vector, len, (const double *)filter_rev, (const double *)window, chunk, (cplx *)dst,
                               (cudaStream_t)stream);
@@ -1300,10 +1335,9 @@ NAPA_API int napafft_filter_chunks(const double *vector, size_t len, const doubl
                                    double *dst) {
     OK(check_filter_args(vector, filter_rev, window, chunk, dst));
     if (len == 0) return NAPA_OK;
-    OK(ensure_init());
-    std::lock_guard<std::mutex> lk(G.mu);
+    OK(napafft_enter());
     OK(ensure_staging(0));
-    cudaStream_t st = G.stream[0];
+    cudaStream_t st = staging().stream[0];
     double *d_vec = nullptr, *d_f = nullptr, *d_w = nullptr; cplx *d_dst = nullptr;
     int rc = NAPA_OK;
     auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == NAPA_OK) rc = fail(NAPA_E_CUDA, "%s", cudaGetErrorString(e)); return e == cudaSuccess; };
@@ -1312,7 +1346,7 @@ NAPA_API int napafft_filter_chunks(const double *vector, size_t len, const doubl
         cu(cudaMemcpyAsync(d_vec, vector, len * 8, cudaMemcpyHostToDevice, st));
         cu(cudaMemcpyAsync(d_f, filter_rev, chunk * 8, cudaMemcpyHostToDevice, st));
         cu(cudaMemcpyAsync(d_w, window, chunk * 8, cudaMemcpyHostToDevice, st));
-        if (rc == NAPA_OK) rc = exec_filter_chunks(d_vec, len, d_f, d_w, chunk, d_dst, st);
+        if (rc == NAPA_OK) rc = LOCKED(exec_filter_chunks(d_vec, len, d_f, d_w, chunk, d_dst, st));
         if (rc == NAPA_OK) cu(cudaMemcpyAsync(dst, d_dst, len * sizeof(cplx), cudaMemcpyDeviceToHost, st));
         cu(cudaStreamSynchronize(st));
     }
@@ -1326,7 +1360,7 @@ NAPA_API int napafft_c2c_cols_dev(const void *src, void *dst, size_t n1, size_t 
     if (src == dst) return fail(NAPA_E_UNSUPPORTED, "column transform is out of place");
     if (!pow2(n1) || !pow2(cols)) return fail(NAPA_E_NOT_POW2, "n1 = %zu / cols = %zu must be powers of two", n1, cols);
     if (dir != NAPA_FWD && dir != NAPA_INV) return fail(NAPA_E_BAD_ENUM, "direction %d is not 1 / -1", dir);
-    OK(ensure_init());
+    OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
     return exec_cols((const cplx *)src, (cplx *)dst, n1, cols, dir, scale, lg_twiddle_modulus, col_offset, (cudaStream_t)stream);
 }
@@ -1334,7 +1368,7 @@ NAPA_API int napafft_c2c_cols_dev(const void *src, void *dst, size_t n1, size_t 
 // dst[r][g][c] = src[g][r][c]   (g < groups, r < rows, c < cols): re-layout around the all-to-all
 NAPA_API int napafft_relayout_dev(const void *src, void *dst, size_t groups, size_t rows, size_t cols, int inverse, void *stream) {
     if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
-    OK(ensure_init());
+    OK(napafft_enter());
     for (size_t g = 0; g < groups; g++) {
         if (!inverse)
             CU(cudaMemcpy2DAsync((char *)dst + g * cols * 16, groups * cols * 16, (const char *)src + g * rows * cols * 16, cols * 16,
@@ -1348,26 +1382,32 @@ NAPA_API int napafft_relayout_dev(const void *src, void *dst, size_t groups, siz
 
 NAPA_API int napafft_dev_alloc(void **out, size_t bytes) {
     if (!out) return fail(NAPA_E_NULL, "out must not be NULL");
-    OK(ensure_init());
+    OK(napafft_enter());
     CU(cudaMalloc(out, bytes ? bytes : 16));
     return NAPA_OK;
 }
-NAPA_API int napafft_dev_free(void *p) { if (p) CU(cudaFree(p)); return NAPA_OK; }
+NAPA_API int napafft_dev_free(void *p) { if (p) { OK(napafft_enter()); CU(cudaFree(p)); } return NAPA_OK; }
 NAPA_API int napafft_dev_upload(void *d, const void *h, size_t bytes) {
     if (!d || !h) return fail(NAPA_E_NULL, "NULL pointer");
+    OK(napafft_enter());
     CU(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
     return NAPA_OK;
 }
 NAPA_API int napafft_dev_download(void *h, const void *d, size_t bytes) {
     if (!d || !h) return fail(NAPA_E_NULL, "NULL pointer");
+    OK(napafft_enter());
     CU(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
     return NAPA_OK;
 }
-NAPA_API int napafft_dev_sync(void) { CU(cudaDeviceSynchronize()); return NAPA_OK; }
+NAPA_API int napafft_dev_sync(void) {
+    OK(napafft_enter());
+    CU(cudaDeviceSynchronize());
+    return LOCKED(check_device_error());
+}
 
 NAPA_API int napafft_host_register(void *ptr, size_t bytes) {
     if (!ptr) return fail(NAPA_E_NULL, "NULL pointer");
-    OK(ensure_init());
+    OK(napafft_enter());
     CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
     return NAPA_OK;
 }
@@ -1382,8 +1422,7 @@ NAPA_API int napafft_c2c(const double *src, double *dst, size_t n, size_t batch,
                          int in_order, const void *window, int window_type, int window_per_batch) {
     OK(check_c2c_args(src, dst, n, batch, stride, dir, scale, window, window_type));
     if (batch == 0) return NAPA_OK;
-    OK(ensure_init());
-    std::lock_guard<std::mutex> lk(G.mu);
+    OK(napafft_enter());
     if (batch == 1) stride = n;
     OK(ensure_staging(16));
     const void *dwin;
@@ -1398,7 +1437,7 @@ NAPA_API int napafft_c2c(const double *src, double *dst, size_t n, size_t batch,
         o.dir = dir; o.in_order = in_order; o.scale = sf;
         o.wtype = window_type; o.wpb = window_per_batch;
         o.window = window_per_batch && dwin ? (const char *)dwin + b0 * n * (window_type == NAPA_WINDOW_REAL ? 8 : 16) : dwin;
-        return exec_c2c((const cplx *)din, (cplx *)dout, n, nb, n, n, o, st);
+        return LOCKED(exec_c2c((const cplx *)din, (cplx *)dout, n, nb, n, n, o, st));
     });
 }
 
@@ -1414,8 +1453,8 @@ static int exec_widen(const void *src, int src_type, cplx *dst, size_t total, cu
 NAPA_API int napafft_widen_dev(const void *src, int src_type, void *dst, size_t count, void *stream) {
     if (!src || !dst) return fail(NAPA_E_NULL, "src/dst must not be NULL");
     if (src_type < 0 || src_type > 3) return fail(NAPA_E_BAD_ENUM, "sample type %d is not 0 .. 3", src_type);
-    OK(ensure_init());
-    return exec_widen(src, src_type, (cplx *)dst, count, (cudaStream_t)stream);
+    OK(napafft_enter());
+    return LOCKED(exec_widen(src, src_type, (cplx *)dst, count, (cudaStream_t)stream));
 }
 // napafft_c2c on an input that still needs complex-samplify: the raw samples cross PCIe, the
 // widening happens on the device.  Items are dense (n samples apart) on both sides.
@@ -1427,8 +1466,7 @@ NAPA_API int napafft_c2c_typed(const void *src, int src_type, double *dst, size_
         return napafft_c2c((const double *)src, dst, n, batch, n, dir, scale, in_order, window, window_type, window_per_batch);
     if ((const void *)src == (const void *)dst) return fail(NAPA_E_UNSUPPORTED, "a typed input cannot alias the complex destination");
     if (batch == 0) return NAPA_OK;
-    OK(ensure_init());
-    std::lock_guard<std::mutex> lk(G.mu);
+    OK(napafft_enter());
     OK(ensure_staging(16));
     const void *dwin;
     OK(upload_window(window, window_type, window_per_batch ? n * batch : n, &dwin));
@@ -1439,12 +1477,12 @@ NAPA_API int napafft_c2c_typed(const void *src, int src_type, double *dst, size_
     j.inplace = false; j.batch = batch;
     const double sf = scale_factor(n, dir, scale);
     return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t b0, cudaStream_t st) -> int {
-        OK(exec_widen(din, src_type, (cplx *)dout, nb * n, st));
+        OK(LOCKED(exec_widen(din, src_type, (cplx *)dout, nb * n, st)));
         C2COpts o{};
         o.dir = dir; o.in_order = in_order; o.scale = sf;
         o.wtype = window_type; o.wpb = window_per_batch;
         o.window = window_per_batch && dwin ? (const char *)dwin + b0 * n * (window_type == NAPA_WINDOW_REAL ? 8 : 16) : dwin;
-        return exec_c2c((const cplx *)dout, (cplx *)dout, n, nb, n, n, o, st);
+        return LOCKED(exec_c2c((const cplx *)dout, (cplx *)dout, n, nb, n, n, o, st));
     });
 }
 
@@ -1454,8 +1492,7 @@ NAPA_API int napafft_bit_reverse(const void *src, void *dst, size_t n, size_t ba
     if (elt != NAPA_ELT_COMPLEX && elt != NAPA_ELT_REAL) return fail(NAPA_E_BAD_ENUM, "element type %d", elt);
     if (batch > 1 && stride < n) return fail(NAPA_E_SHORT_BUFFER, "stride %zu shorter than n %zu", stride, n);
     if (batch == 0) return NAPA_OK;
-    OK(ensure_init());
-    std::lock_guard<std::mutex> lk(G.mu);
+    OK(napafft_enter());
     if (batch == 1) stride = n;
     const size_t es = elt == NAPA_ELT_COMPLEX ? 16 : 8;
     HostJob j;
@@ -1463,35 +1500,33 @@ NAPA_API int napafft_bit_reverse(const void *src, void *dst, size_t n, size_t ba
     j.dst = (char *)dst; j.out_item_bytes = n * es; j.out_pitch = stride * es;
     j.inplace = true; j.batch = batch;
     return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
-        return exec_bitrev(din, dout, n, nb, n, n, elt, st);
+        return LOCKED(exec_bitrev(din, dout, n, nb, n, n, elt, st));
     });
 }
 
 NAPA_API int napafft_rfft(const double *src, double *dst, size_t n, size_t batch, int scale) {
     OK(check_real_args(src, dst, n, scale));
     if (batch == 0) return NAPA_OK;
-    OK(ensure_init());
-    std::lock_guard<std::mutex> lk(G.mu);
+    OK(napafft_enter());
     HostJob j;
     j.src = (const char *)src; j.in_item_bytes = n * 8; j.in_pitch = n * 8;
     j.dst = (char *)dst; j.out_item_bytes = n * 16; j.out_pitch = n * 16;
     j.batch = batch;
     return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
-        return exec_rfft((const double *)din, (cplx *)dout, n, nb, scale, st);
+        return LOCKED(exec_rfft((const double *)din, (cplx *)dout, n, nb, scale, st));
     });
 }
 
 NAPA_API int napafft_rifft(const double *src, double *dst, size_t n, size_t batch, int scale) {
     OK(check_real_args(src, dst, n, scale));
     if (batch == 0) return NAPA_OK;
-    OK(ensure_init());
-    std::lock_guard<std::mutex> lk(G.mu);
+    OK(napafft_enter());
     HostJob j;
     j.src = (const char *)src; j.in_item_bytes = n * 16; j.in_pitch = n * 16;
     j.dst = (char *)dst; j.out_item_bytes = n * 8; j.out_pitch = n * 8;
     j.batch = batch;
     return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
-        return exec_rifft((const cplx *)din, (double *)dout, n, nb, scale, st);
+        return LOCKED(exec_rifft((const cplx *)din, (double *)dout, n, nb, scale, st));
     });
 }
 
@@ -1499,13 +1534,12 @@ NAPA_API int napafft_2rfft(const double *v1, const double *v2, double *dst, size
     OK(check_real_args(v1, dst, n, scale));
     if (!v2) return fail(NAPA_E_NULL, "v2 must not be NULL");
     if (batch == 0) return NAPA_OK;
-    OK(ensure_init());
-    std::lock_guard<std::mutex> lk(G.mu);
+    OK(napafft_enter());
     HostJob j;
     j.src = (const char *)v1; j.src2 = (const char *)v2; j.in_item_bytes = n * 8; j.in_pitch = n * 8;
     j.dst = (char *)dst; j.out_item_bytes = 2 * n * 16; j.out_pitch = 2 * n * 16;
     j.batch = batch;
     return run_host_job(j, [&](char *din, char *dout, size_t nb, size_t, cudaStream_t st) -> int {
-        return exec_2rfft((const double *)din, (const double *)(din + nb * n * 8), (cplx *)dout, n, nb, scale, st);
+        return LOCKED(exec_2rfft((const double *)din, (const double *)(din + nb * n * 8), (cplx *)dout, n, nb, scale, st));
     });
 }

@@ -541,15 +541,36 @@ class NapaFFT:
         return self.rifft(vec, dst=dst, size=size, scale=True)
 
     # ---- new exports: batched host arrays (H5: the reference has no batch parameter) ------
+    @staticmethod
+    def _check_batch(x, dtype, what):
+        if not (isinstance(x, np.ndarray) and x.ndim == 2 and x.dtype == dtype and x.flags.c_contiguous):
+            raise TypeError(f"{what} must be a C-contiguous (batch, n) array of {np.dtype(dtype).name}")
+        if not power_of_two_p(x.shape[1]):
+            raise NapaFFTError(1, f"size {x.shape[1]} is not a power of two")
+
+    @staticmethod
+    def _check_out(out, shape, dtype):
+        if not (isinstance(out, np.ndarray) and out.shape == tuple(shape) and out.dtype == dtype and out.flags.c_contiguous
+                and out.flags.writeable):
+            raise TypeError(f"out must be a writable C-contiguous {tuple(shape)} array of {np.dtype(dtype).name}")
+
     def fft_batch(self, x, direction=1, in_order=True, scale=None, window=None, out=None):
-        """x: (batch, n) complex128, C-contiguous; one call, one staging pipeline."""
-        assert x.ndim == 2 and x.dtype == np.complex128 and x.flags.c_contiguous
+        """x: (batch, n) complex128, C-contiguous; one call, one staging pipeline.  `window`: n weights shared by the
+        batch, or (batch, n) weights, float64 or complex128 (the C ABI takes raw pointers: everything is checked here)."""
+        self._check_batch(x, np.complex128, "x")
         batch, n = x.shape
-        out = x if out is None else out
+        if out is None:
+            out = x
+        else:
+            self._check_out(out, x.shape, np.complex128)
         wpb = 0
-        wptr, wt = None, 0
+        wptr, wt, w = None, 0, None
         if window is not None:
             w = np.ascontiguousarray(window)
+            if w.dtype not in (np.float64, np.complex128):
+                raise TypeError("window must be float64 (real-sample-array) or complex128 (complex-sample-array)")
+            if w.ndim not in (1, 2) or w.shape[-1] < n or (w.ndim == 2 and w.shape != (batch, n)):
+                raise NapaFFTError(2, f"window of shape {w.shape} does not cover {batch} transform(s) of {n} points")
             wt = _lib.WINDOW_COMPLEX if w.dtype == np.complex128 else _lib.WINDOW_REAL
             wpb = int(w.ndim == 2)
             wptr = _ptr(w)
@@ -558,23 +579,34 @@ class NapaFFT:
         return out
 
     def rfft_batch(self, x, scale=None, out=None):
-        assert x.ndim == 2 and x.dtype == np.float64 and x.flags.c_contiguous
+        self._check_batch(x, np.float64, "x")
         batch, n = x.shape
-        out = np.empty((batch, n), dtype=np.complex128) if out is None else out
+        if out is None:
+            out = np.empty((batch, n), dtype=np.complex128)
+        else:
+            self._check_out(out, (batch, n), np.complex128)
         self.b.rfft(_ptr(x), _ptr(out), n, batch, _scale_code(scale))
         return out
 
     def rifft_batch(self, x, scale=True, out=None):
-        assert x.ndim == 2 and x.dtype == np.complex128 and x.flags.c_contiguous
+        self._check_batch(x, np.complex128, "x")
         batch, n = x.shape
-        out = np.empty((batch, n), dtype=np.float64) if out is None else out
+        if out is None:
+            out = np.empty((batch, n), dtype=np.float64)
+        else:
+            self._check_out(out, (batch, n), np.float64)
         self.b.rifft(_ptr(x), _ptr(out), n, batch, _scale_code(scale))
         return out
 
     def bit_reverse_batch(self, x, out=None):
-        assert x.ndim == 2 and x.flags.c_contiguous and x.dtype in (np.complex128, np.float64)
+        if not (isinstance(x, np.ndarray) and x.dtype in (np.complex128, np.float64)):
+            raise TypeError("x must be a (batch, n) array of complex128 or float64")
+        self._check_batch(x, x.dtype, "x")
         batch, n = x.shape
-        out = x if out is None else out
+        if out is None:
+            out = x
+        else:
+            self._check_out(out, x.shape, x.dtype)
         self.b.bit_reverse(_ptr(x), _ptr(out), n, batch, n,
                            _lib.ELT_COMPLEX if x.dtype == np.complex128 else _lib.ELT_REAL)
         return out
