@@ -4,11 +4,15 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
 
 A STEP is one pass of the hot path over one batch of synthetic input already resident in HBM.
-Default workload (N = 1) is BASELINE.json configs[1] ("c2"): 4096 x 2^16 complex doubles,
-windowed-fft (shared Hann window, :in-order t) followed by ifft :scale :inv (:in-order t).
+Default workload is BASELINE.json configs[2] ("c3"), the largest single-GPU configuration and the one the
+>= 70 % HBM-roofline target of `north_star` is stated on: 1024 x 2^20 complex doubles, fft :in-order nil followed by
+ifft :in-order nil with a shared complex window (the convolution building block).  A short measurement of c2
+(4096 x 2^16, the config `metric` is quoted on) and c4 rides along in `other_workloads`.
 Metric: FP64 complex FFT GFLOP/s = 5 N log2 N per transform / time (BASELINE.json `metric`).
 N > 1: one process per GPU (torchrun), the batch is sharded with no data-path collective
-(weak scaling: every GPU gets the full per-GPU batch); time = max over ranks.
+(weak scaling: every GPU gets the full per-GPU batch); time = max over ranks.  The line then also carries a `dist`
+record: ONE 2^(27 + log2 N)-point transform spread over the N GPUs (config c5: distributed four-step, NCCL
+all-to-all over NVLink), with its time, the exchange alone and a parity figure.
 """
 import argparse
 import ctypes as C
@@ -204,11 +208,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="napa", choices=["napa", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_workloads / dist riders")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "napa" else args.warmup
 
@@ -246,6 +251,102 @@ def main():
     if wl == "c5":
         run_c5(args, torch, dist, napa, b, world, rank, local, dev)
         return
+    m = measure_workload(args, torch, dist, napa, b, wl, world, rank, local, dev, args.steps, args.warmup)
+    ms_per_step, launches, clocks, parity, win = m["ms_per_step"], m["launches"], m["clocks"], m["parity"], m["win"]
+    value = flops_per_step(wl) * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (fft_pass_kernel) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = algorithmic_bytes_per_step(wl) / (ms_per_step * 1e-3) / 1e9
+    launches_per_step = launches / max(args.steps, 1)
+    traffic, traffic_src = None, None
+    try:
+        # DRAM bytes of one whole step summed over its launches, from this round's `ncu --set full` capture of the same
+        # command (tools/profile_c2.sh writes the file next to the summaries it comes from), per launch like `achieved`
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(wl)
+        traffic = float(t["dram_bytes_per_step"]) / max(launches_per_step, 1)
+        traffic_src = t.get("source")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "napa::fft_pass_kernel<LOG2L,KIND,LEAN> (one launch per digit pass; two per 2^14..2^22 transform)",
+                "algorithmic_bytes_per_launch": algorithmic_bytes_per_step(wl) / max(launches_per_step, 1),
+                "avg_launch_ms": ms_per_step / max(launches_per_step, 1),
+                "frac_of_nominal_8000": achieved / 8000.0}
+
+    # ---- e2e: the same step through the host-buffer C ABI (pinned host arrays, PCIe inside) ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, torch, dist, napa, b, wl, world, dev, win)
+        except Exception as ex:  # report, never fake
+            e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:200]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        items = min(batch, 2 * (os.cpu_count() or 1))
+        threads = max(1, min(os.cpu_count() or 1, items))       # threads actually used (1 for the single-transform config)
+        st = cpu_oracle_state(wl, items)
+        cpu_oracle_step(wl, items, threads, st)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 8.0 and reps < 50:
+            cpu_oracle_step(wl, items, threads, st); reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": flops_per_step(wl) * (items / batch) / dt / 1e9, "unit": "GFLOP/s", "cores": threads,
+                        "kind": "port",
+                        "sample": "%d of %d transforms per step, %d reps, batch-parallel over %d threads; oracle = C "
+                                  "restatement of Napa-FFT3 (SBCL unavailable)" % (items, batch, reps, threads)}
+
+    # ---- riders: the other single-GPU configs (short runs) and, for N > 1, the distributed transform ----
+    others, dist_rec = None, None
+    if not args.no_extras:
+        others = {}
+        for w2 in ("c2", "c4"):
+            if w2 == wl:
+                continue
+            try:
+                m2 = measure_workload(args, torch, dist, napa, b, w2, world, rank, local, dev, max(5, args.steps // 5), 3, clocks=False)
+                a2 = algorithmic_bytes_per_step(w2) / (m2["ms_per_step"] * 1e-3) / 1e9
+                others[w2] = {"description": WORKLOADS[w2][2], "ms_per_step": m2["ms_per_step"], "steps": m2["steps"],
+                              "value": flops_per_step(w2) * world / (m2["ms_per_step"] * 1e-3) / 1e9, "unit": "GFLOP/s",
+                              "roofline_frac": a2 / peak, "parity_nre_vs_oracle": m2["parity"]}
+            except Exception as ex:
+                others[w2] = {"error": str(ex)[:200]}
+        if world > 1:
+            try:
+                lg = 27 + int(np.log2(world))
+                dist_rec = measure_c5(args, torch, dist, napa, b, world, rank, local, dev, lg, max(5, args.steps // 5), 3)
+            except Exception as ex:
+                dist_rec = {"error": str(ex)[:300]}
+
+    if rank == 0:
+        line = {
+            "metric": "fp64_complex_fft_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch},
+            "timing": {"l2_policy": "inputs_exceed_l2 (%.1f GiB per array per GPU)" % (16.0 * n * batch / 2**30),
+                       "sharding": "batch-sharded, no collective" if world > 1 else "single GPU",
+                       "clock": "CUDA events on the launching stream, max over ranks"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "parity_nre_vs_oracle": parity,
+            "other_workloads": others, "dist": dist_rec,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_workload(args, torch, dist, napa, b, wl, world, rank, local, dev, steps, warmup, clocks=True):
+    """`steps` timed steps of workload `wl` on device-resident synthetic data; the inputs are freed on return."""
+    n, batch, desc = WORKLOADS[wl]
     stream = torch.cuda.current_stream().cuda_stream
     g = torch.Generator(device=dev); g.manual_seed(1002 + rank)
 
@@ -288,10 +389,11 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    if clocks:
+        sampler.start()
+        time.sleep(0.3)
     t_warm = time.perf_counter()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     launches0 = b.launch_count()
@@ -299,24 +401,24 @@ def main():
     barrier()
     t_begin = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     barrier()
     t_end = time.perf_counter()
     launches = b.launch_count() - launches0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t_begin, t_end)
-    clocks["window"] = "timed region"
-    if not clocks.get("samples") or clocks["samples"] < 3:
-        clocks = sampler.summarise(t_warm, t_end)
-        clocks["window"] = "warm-up + timed region (timed region shorter than 3 samples at 100 ms)"
+    clk = None
+    if clocks:
+        clk = sampler.stop(t_begin, t_end)
+        clk["window"] = "timed region"
+        if not clk.get("samples") or clk["samples"] < 3:
+            clk = sampler.summarise(t_warm, t_end)
+            clk["window"] = "warm-up + timed region (timed region shorter than 3 samples at 100 ms)"
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
-    ms_per_step = ms / args.steps
-    value = flops_per_step(wl) * world / (ms_per_step * 1e-3) / 1e9
 
     # ---- quick self-check of the timed path against the oracle (not timed) ----
     parity = None
@@ -333,76 +435,22 @@ def main():
             want = O.fft(x[i].cpu().numpy())
         got = (y if wl == "c1" else z)[i].cpu().numpy()
         parity = float(np.linalg.norm(got - want) / np.linalg.norm(want))
-
-    # ---- roofline of the dominant kernel (fft_pass_kernel) ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    achieved = algorithmic_bytes_per_step(wl) / (ms_per_step * 1e-3) / 1e9
-    launches_per_step = launches / max(args.steps, 1)
-    traffic = None
-    try:
-        # measured DRAM bytes of one whole step (sum over its launches, ncu --set full), per launch like `achieved`
-        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(wl)
-        traffic = float(t["dram_bytes_per_step"]) / max(launches_per_step, 1)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "napa::fft_pass_kernel<LOG2L,KIND,LEAN> (one launch per digit pass; two per 2^14..2^20 transform)",
-                "algorithmic_bytes_per_launch": algorithmic_bytes_per_step(wl) / max(launches_per_step, 1),
-                "avg_launch_ms": ms_per_step / max(launches_per_step, 1),
-                "frac_of_nominal_8000": achieved / 8000.0}
-
-    # ---- e2e: the same step through the host-buffer C ABI (pinned host arrays, PCIe inside) ----
-    e2e = None
-    if not args.no_e2e:
-        try:
-            e2e = run_e2e(args, torch, dist, napa, b, wl, world, dev, win)
-        except Exception as ex:  # report, never fake
-            e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:200]}
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        items = min(batch, 2 * (os.cpu_count() or 1))
-        threads = max(1, min(os.cpu_count() or 1, items))       # threads actually used (1 for the single-transform config)
-        st = cpu_oracle_state(wl, items)
-        cpu_oracle_step(wl, items, threads, st)
-        t0 = time.perf_counter(); reps = 0
-        while time.perf_counter() - t0 < 8.0 and reps < 50:
-            cpu_oracle_step(wl, items, threads, st); reps += 1
-        dt = (time.perf_counter() - t0) / reps
-        cpu_baseline = {"value": flops_per_step(wl) * (items / batch) / dt / 1e9, "unit": "GFLOP/s", "cores": threads,
-                        "kind": "port",
-                        "sample": "%d of %d transforms per step, %d reps, batch-parallel over %d threads; oracle = C "
-                                  "restatement of Napa-FFT3 (SBCL unavailable)" % (items, batch, reps, threads)}
-
-    if rank == 0:
-        line = {
-            "metric": "fp64_complex_fft_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch,
-                       "l2_policy": "inputs_exceed_l2 (%.1f GiB per array per GPU)" % (x.numel() * x.element_size() / 2**30),
-                       "sharding": "batch-sharded, no collective" if world > 1 else "single GPU"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity_nre_vs_oracle": parity,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    win_host = win.cpu() if win is not None else None
+    del x, y, z
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms / steps, "steps": steps, "launches": launches, "clocks": clk, "parity": parity, "win": win_host}
 
 
-def run_c5(args, torch, dist, napa, b, world, rank, local, dev):
-    """BASELINE config C5: ONE 2^lg transform over all ranks (strong scaling: total work fixed).
-    Device-resident distributed layouts (napa_fft3_b200.dist.DistributedFFT); time = max over ranks."""
+def measure_c5(args, torch, dist, napa, b, world, rank, local, dev, lg, steps, warmup):
+    """ONE 2^lg-point transform over all ranks (distributed four-step, napa_fft3_b200.dist.DistributedFFT over
+    napafft_dist_c2c_dev); time = max over ranks.  Parity: the input is a handful of impulses, so every bin is known in
+    closed form; a sample of local bins is compared (normwise, against the 1e-13 log2 N tolerance)."""
     from napa_fft3_b200.dist import DistributedFFT
-    lg = int(os.environ.get("NAPAFFT_C5_LOG2N", "30"))
     n = 1 << lg
     f = DistributedFFT(lg, b, dist if world > 1 else None, dev)
+    rng = np.random.Generator(np.random.Philox(1005))
+    pos = np.unique(np.concatenate([[0, 1, n - 1, n // 2 + 1], rng.integers(0, n, 28)]))
+    amp = rng.uniform(-1, 1, len(pos)) + 1j * rng.uniform(-1, 1, len(pos))
     g = torch.Generator(device=dev); g.manual_seed(1005 + rank)
     x = torch.view_as_complex(torch.rand((f.N1, f.B, 2), dtype=torch.float64, device=dev, generator=g) * 2 - 1).contiguous()
     out = torch.empty((f.R, f.N2), dtype=torch.complex128, device=dev)
@@ -412,7 +460,7 @@ def run_c5(args, torch, dist, napa, b, world, rank, local, dev):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         f.forward(x, out)
     barrier()
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
@@ -421,7 +469,7 @@ def run_c5(args, torch, dist, napa, b, world, rank, local, dev):
     barrier()
     t_begin = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         f.forward(x, out)
     e1.record()
     barrier()
@@ -429,49 +477,83 @@ def run_c5(args, torch, dist, napa, b, world, rank, local, dev):
     launches = b.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t_begin, t_end)
-    # exchange alone (same buffers), for the NVLink roofline
+    # the exchange alone (torch.distributed all_to_all_single on buffers of the same size), for the NVLink roofline
+    f.exchange_only(2)
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     a0.record()
-    for _ in range(args.steps):
-        f._exchange(f.recv, f.send)
+    f.exchange_only(steps)
     a1.record()
     barrier()
-    a2a_ms = a0.elapsed_time(a1) / args.steps
+    a2a_ms = a0.elapsed_time(a1) / steps
     if world > 1:
         t = torch.tensor([ms, a2a_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, a2a_ms = t[0].item(), t[1].item()
-    ms_per_step = ms / args.steps
-    # parity: round trip + a sample of bins against a direct DFT of the (regenerated) input is
-    # done in tests/tools (dist_check.py); here only the round-trip residual
-    back = f.inverse(out)
+    ms_per_step = ms / steps
+    # parity (not timed): impulses in, closed-form spectrum on sampled local bins; then the round trip of the random input
+    xi = torch.zeros((f.N1, f.B), dtype=torch.complex128, device=dev)
+    for p_, a_ in zip(pos, amp):
+        j1, j2 = divmod(int(p_), f.N2)
+        if f.rank * f.B <= j2 < (f.rank + 1) * f.B:
+            xi[j1, j2 - f.rank * f.B] = complex(a_)
+    Xi = f.forward(xi)
+    sel = rng.integers(0, f.R * f.N2, 400)
+    k = (f.rank * f.R + sel // f.N2) + f.N1 * (sel % f.N2)
+    ph = (pos[None, :].astype(object) * k[:, None].astype(object)) % n
+    want = (amp[None, :] * np.exp(-2j * np.pi * ph.astype(np.float64) / n)).sum(axis=1)
+    got = Xi.view(-1)[torch.from_numpy(sel).to(dev)].cpu().numpy()
+    nre = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    back = f.inverse(f.forward(x, out))
     rt = (torch.linalg.norm(back - x) / torch.linalg.norm(x)).item()
+    if world > 1:
+        t = torch.tensor([nre, rt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nre, rt = t[0].item(), t[1].item()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_bytes = 32.0 * n / world                      # compulsory HBM bytes per GPU
+    a2a_bytes = f.alltoall_bytes_per_rank()
+    rec = {
+        "workload": "c5", "description": WORKLOADS["c5"][2], "log2n": lg, "n": n, "N1": f.N1, "N2": f.N2, "n_gpus": world,
+        "exchange": "library-owned NCCL communicator (napafft_dist_c2c_dev), %d column chunks" % f.nch if f.native else "torch.distributed per chunk",
+        "ms_per_step": ms_per_step, "steps": steps, "value": 5.0 * n * lg / (ms_per_step * 1e-3) / 1e9, "unit": "GFLOP/s",
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": hbm_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None,
+                     "note": "per-GPU compulsory bytes (32 N / P) over the whole step, all-to-all included"},
+        "nvlink": {"alltoall_bytes_per_gpu_each_way": a2a_bytes, "alltoall_alone_ms": a2a_ms,
+                   "alltoall_alone_gbs_per_direction": (a2a_bytes / (a2a_ms * 1e-3) / 1e9) if a2a_ms > 0 and world > 1 else None,
+                   "whole_transform_gbs_per_direction": (a2a_bytes / (ms_per_step * 1e-3) / 1e9) if world > 1 else None,
+                   "peak_measured_ref": 770.0, "peak_nominal": 900.0,
+                   "frac_of_measured_alltoall_alone": (a2a_bytes / (a2a_ms * 1e-3) / 1e9 / 770.0) if a2a_ms > 0 and world > 1 else None,
+                   "frac_of_measured_whole_transform": (a2a_bytes / (ms_per_step * 1e-3) / 1e9 / 770.0) if world > 1 else None},
+        "parity_nre_vs_closed_form": nre, "round_trip_nre": rt, "tolerance": 1e-13 * lg,
+    }
+    del x, out, xi, Xi, back
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_c5(args, torch, dist, napa, b, world, rank, local, dev):
+    """BASELINE config C5 as the main workload: strong scaling (total work fixed)."""
+    lg = int(os.environ.get("NAPAFFT_C5_LOG2N", "30"))
+    rec = measure_c5(args, torch, dist, napa, b, world, rank, local, dev, lg, args.steps, args.warmup)
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_bytes = 32.0 * n / world                      # compulsory HBM bytes per GPU
-        a2a_bytes = f.alltoall_bytes_per_rank()
         line = {
-            "metric": "fp64_complex_fft_gflops", "value": 5.0 * n * lg / (ms_per_step * 1e-3) / 1e9, "unit": "GFLOP/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "metric": "fp64_complex_fft_gflops", "value": rec["value"], "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c5", "description": WORKLOADS["c5"][2], "n": n, "N1": f.N1, "N2": f.N2,
-                       "layout": "time side: column block of [N1][N2]; freq side: row block k1 of X[k1 + N1*k2]",
-                       "l2_policy": "inputs_exceed_l2 (%.1f GiB per GPU)" % (16.0 * n / world / 2**30)},
-            "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": hbm_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None,
-                         "note": "per-GPU compulsory bytes (32 N / P) over the whole step, all-to-all included"},
-            "nvlink": {"alltoall_bytes_per_gpu_each_way": a2a_bytes, "alltoall_ms": a2a_ms,
-                       "achieved_gbs_per_direction": (a2a_bytes / (a2a_ms * 1e-3) / 1e9) if a2a_ms > 0 and world > 1 else None,
-                       "peak_measured_ref": 770.0, "peak_nominal": 900.0,
-                       "frac_of_measured": (a2a_bytes / (a2a_ms * 1e-3) / 1e9 / 770.0) if a2a_ms > 0 and world > 1 else None},
-            "cpu_baseline": None, "round_trip_nre": rt,
+            "config": {"workload": "c5", "description": WORKLOADS["c5"][2], "n": rec["n"], "batch_per_gpu": 1},
+            "timing": {"l2_policy": "inputs_exceed_l2 (%.1f GiB per GPU)" % (16.0 * rec["n"] / world / 2**30),
+                       "layout": "time side: column block of [N1][N2]; freq side: row block k1 of X[k1 + N1*k2]"},
+            "clocks": rec["clocks"], "e2e": None, "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"],
+            "nvlink": rec["nvlink"], "cpu_baseline": None, "parity_nre_vs_closed_form": rec["parity_nre_vs_closed_form"],
+            "round_trip_nre": rec["round_trip_nre"], "dist": rec,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -496,7 +578,7 @@ def run_e2e(args, torch, dist, napa, b, wl, world, dev, win):
         chunk = max(1, (1 << 24) // n)
         for i in range(0, batch, chunk):
             v[i:i + chunk] = rng.uniform(-1, 1, v[i:i + chunk].shape)
-    hwin = win.cpu().numpy() if win is not None else None
+    hwin = win.numpy() if win is not None else None
     x, y, z = hx.numpy(), hy.numpy(), hz.numpy()
 
     def step():

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NAPAFFT_ABI_VERSION 1
+#define NAPAFFT_ABI_VERSION 2
 
 typedef enum {
     NAPA_OK = 0,
@@ -146,6 +146,31 @@ int napafft_cmul_dev(void *a, const void *h, size_t n, size_t batch, size_t h_st
 int napafft_c2c_cols_dev(const void *src, void *dst, size_t n1, size_t cols, int dir, double scale,
                          int lg_twiddle_modulus, long long col_offset, void *stream);
 int napafft_relayout_dev(const void *src, void *dst, size_t groups, size_t rows, size_t cols, int inverse, void *stream);
+
+/* ---- one transform over several GPUs (BASELINE config 5; replaces nothing in the reference, which is single-process:
+ * it is what a caller of (fft vec) gets for a vector too large for one device; boundary = interface.lisp:165-189 get-fft) ----
+ * One process per GPU.  N = 2^lgN = N1 * N2 with N1 = 2^(lgN/2); x[j1*N2 + j2] is an [N1][N2] matrix.
+ *   time layout, rank g of P:  columns j2 in [g*B, (g+1)*B), B = N2/P, as a dense local [N1][B] array;
+ *   freq layout, rank h:       rows k1 in [h*R, (h+1)*R), R = N1/P, of X[k1 + N1*k2], as a dense local [R][N2] array.
+ * napafft_dist_c2c(_dev): dir = 1 maps the time layout to the freq layout (unscaled DFT), dir = -1 maps back and scales
+ * by 1/N.  Out of place.  The library owns the NCCL communicator (bound at run time from libnccl.so.2; failures are
+ * NAPA_E_NCCL): rank 0 calls napafft_dist_unique_id and hands the 128 bytes to the other ranks by any means, then every
+ * rank calls napafft_dist_init(id, rank, nranks) after napafft_init(device).  nranks = 1 needs no NCCL. */
+int napafft_dist_unique_id(void *out128);
+int napafft_dist_init(const void *unique_id128, int rank, int nranks);
+int napafft_dist_shutdown(void);
+int napafft_dist_c2c_dev(const void *src_local, void *dst_local, int lgN, int dir, void *stream);
+int napafft_dist_c2c(const double *src_local, double *dst_local, int lgN, int dir);
+/* geometry of the layouts above for 2^lgN points over nranks ranks (any output pointer may be NULL) */
+int napafft_dist_geometry(int lgN, int nranks, size_t *n1, size_t *n2, size_t *cols_per_rank, size_t *rows_per_rank,
+                          int *nchunks);
+/* The two local stages, for hosts that carry the exchange with their own communicator: the exchange buffer xbuf is
+ * [nchunks][N1][Bc] (Bc = B / nchunks): chunk c holds the columns [c*Bc, (c+1)*Bc) of every row; its P slabs of R rows
+ * are the messages of an all-to-all (slab h goes to rank h), delivered into the same place of the receiver's buffer.
+ *   cols: dir = 1: x_local [N1][B] -> chunk `chunk` of xbuf (column FFTs + global twiddle);  dir = -1: the inverse.
+ *   rows: dir = 1: received xbuf -> X_local [R][N2] (row FFTs read the exchange layout directly);  dir = -1: the inverse. */
+int napafft_dist_cols_dev(void *x_local, void *xbuf, int lgN, int nranks, int rank, int chunk, int dir, void *stream);
+int napafft_dist_rows_dev(void *xbuf, void *X_local, int lgN, int nranks, int dir, void *stream);
 
 /* plain device-memory helpers so that a non-CUDA host (SBCL) can hold device-resident vectors */
 int napafft_dev_alloc(void **out, size_t bytes);

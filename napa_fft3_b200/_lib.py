@@ -28,6 +28,8 @@ ABI_SYMBOLS = [
     "napafft_c2c_dev", "napafft_bit_reverse_dev", "napafft_rfft_dev", "napafft_rifft_dev", "napafft_2rfft_dev",
     "napafft_cmul_dev", "napafft_c2c_cols_dev", "napafft_relayout_dev", "napafft_dev_alloc", "napafft_dev_free", "napafft_dev_upload", "napafft_dev_download",
     "napafft_dev_sync", "napafft_scale_factor", "napafft_radix2_twiddle",
+    "napafft_dist_unique_id", "napafft_dist_init", "napafft_dist_shutdown", "napafft_dist_c2c_dev", "napafft_dist_c2c",
+    "napafft_dist_geometry", "napafft_dist_cols_dev", "napafft_dist_rows_dev",
 ]
 
 
@@ -76,6 +78,13 @@ class Binding:
         L.napafft_dev_free.argtypes = [vp]
         L.napafft_dev_upload.argtypes = [vp, vp, sz]
         L.napafft_dev_download.argtypes = [vp, vp, sz]
+        L.napafft_dist_unique_id.argtypes = [vp]
+        L.napafft_dist_init.argtypes = [vp, i, i]
+        L.napafft_dist_c2c_dev.argtypes = [vp, vp, i, i, vp]
+        L.napafft_dist_c2c.argtypes = [vp, vp, i, i]
+        L.napafft_dist_geometry.argtypes = [i, i, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(i)]
+        L.napafft_dist_cols_dev.argtypes = [vp, vp, i, i, i, i, i, vp]
+        L.napafft_dist_rows_dev.argtypes = [vp, vp, i, i, i, vp]
         L.napafft_scale_factor.restype = d
         L.napafft_scale_factor.argtypes = [sz, i, i]
         L.napafft_radix2_twiddle.argtypes = [sz, i, vp]

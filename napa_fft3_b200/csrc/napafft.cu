@@ -91,6 +91,7 @@ struct State {
     int fused_prefetch = 1;               // L2 prefetch of each CTA's next pass-A tile
     int fused_tma = 0;                    // NAPAFFT_FUSED_TMA=1: TMA-fed warp-specialised variant of the fused kernel (2^14 .. 2^16)
     int fused_lead = 0;                   // units pass A runs ahead of pass B (0 = default 2)
+    int dist_chunks = 4;                  // distributed four-step: column chunks whose exchange overlaps the next chunk's column FFTs
     bool use_fused = false;               // fused single-launch plans for 2^14 .. 2^20 (NAPAFFT_FUSED=1); measured: no faster than one launch per digit pass
     bool attrs_set = false;
     int num_sms = 148;
@@ -517,7 +518,15 @@ struct C2COpts {
     bool rifft_pre = false; const cplx *r2tw = nullptr;
     bool rfft_post = false;    // single-pass only: fuse the rfft epilogue into the store (dst stride = 2n)
     const double *zip_im = nullptr;   // single-pass only (%2rfft): src is a REAL vector, zip_im the second one; split epilogue in the store
+    // distributed four-step: the rows are read from (split_in) / written to (split_out) the exchange layout
+    // [chunk][rank][row][Bc] instead of a dense [row][n] matrix (napafft_kernels.cuh: split_offset); natural order only
+    bool split_in = false, split_out = false;
+    int sp_lgbc = 0, sp_lgnch = 0; long long sp_chunk_stride = 0, sp_rank_stride = 0;
 };
+static void apply_split(PassParams &p, const C2COpts &o, bool in) {
+    p.flags |= in ? napa::PF_SPLIT_IN : napa::PF_SPLIT_OUT;
+    p.sp_lgbc = o.sp_lgbc; p.sp_lgnch = o.sp_lgnch; p.sp_chunk_stride = o.sp_chunk_stride; p.sp_rank_stride = o.sp_rank_stride;
+}
 
 // geometry of digit pass s (0-based) of an item with digits d[0..p)
 static void pass_geometry(const std::vector<int> &d, int s, PassParams &p, long long *tiles_per_item) {
@@ -566,6 +575,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     // window index is the bit-reversed position for an in-order inverse (easy-interface.lisp:83-95)
     const bool win_rev = inv && o.in_order;
 
+    if (lg <= 3 && (o.split_in || o.split_out)) return fail(NAPA_E_UNSUPPORTED, "the exchange layout needs rows of at least 16 points");
     if (lg <= 3) {
         napa::TinyParams t{};
         t.src = src; t.dst = dst; t.src_batch_stride = (long long)sstride; t.dst_batch_stride = (long long)dstride;
@@ -600,6 +610,8 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
         first_pass_fusions(pp, o, n, win_rev);
         if (o.rfft_post) { pp.flags |= napa::PF_RFFT_POST; pp.r2tw = o.r2tw; }
         if (o.zip_im) { pp.flags |= napa::PF_ZIP2 | napa::PF_SPLIT2_POST; pp.src_im = o.zip_im; }
+        if (o.split_in) apply_split(pp, o, true);
+        if (o.split_out) apply_split(pp, o, false);
         const long long C = 1LL << napa::plan_log2c(lg);
         OK(launch_pass(lg, KIND_ROW, pp, ((long long)batch + C - 1) / C, st));
         CU(cudaGetLastError());
@@ -611,7 +623,9 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     chunk = std::min(chunk, batch);
 
     const bool natural = o.in_order != 0;
-    const int fcol = G.use_fused ? fused_col_digit(lg) : 0;
+    if ((o.split_in || o.split_out) && (p > 2 || !natural))
+        return fail(NAPA_E_UNSUPPORTED, "the exchange layout is supported for natural-order rows of 2^4 .. 2^22 points");
+    const int fcol = G.use_fused && !o.split_in && !o.split_out ? fused_col_digit(lg) : 0;
     if (fcol && !getenv("NAPAFFT_DIGITS")) {
         // one persistent launch for the whole batch, the intermediate stays in L2 (napafft_kernels.cuh: fft_fused_kernel)
         const std::vector<int> fd = { fcol, lg - fcol };
@@ -666,6 +680,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
     // that (> max_scratch_bytes, 2^31 and up by default) falls back to the in-place bit-reversed
     // pipeline plus the in-place bit-reversal pass, which needs no extra memory.
     const bool nat_scratch = natural && chunk * n * sizeof(cplx) <= G.max_scratch_bytes;
+    if ((o.split_in || o.split_out) && !nat_scratch) return fail(NAPA_E_UNSUPPORTED, "the exchange layout needs the scratch copy");
     if (nat_scratch) {
         // natural in -> natural out, one HBM pass per digit and no separate bit-reversal pass:
         //   p == 2: column pass src -> scratch [k1][n2], row pass scratch -> dst stored transposed (k1 + L1 k2)
@@ -693,6 +708,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
                 p1.tw_lo = bt.lo; p1.tw_hi = bt.hi; p1.tw_shift = bt.shift; p1.tw_mask = (1ull << (d[s] + lgB)) - 1;
                 if (s == 0) {
                     if (o.zip_im) { p1.flags |= napa::PF_ZIP2; p1.src_im = o.zip_im + b0 * sstride; }
+                    if (o.split_in) apply_split(p1, o, true);
                     first_pass_fusions(p1, o, n, win_rev);
                     if (o.wpb && o.wtype) p1.window = (const char *)o.window + b0 * n * (o.wtype == NAPA_WINDOW_REAL ? 8 : 16);
                 }
@@ -710,6 +726,7 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
             p2.flags = inv ? napa::PF_CONJ_OUT : 0;
             // row r = ra*C + q holds the leading output digits (k1 + L1 k2); output k_last -> address r + (n / L_last) * k_last
             p2.d_SA = 1LL << napa::plan_log2c(d[p - 1]); p2.d_SG = 0; p2.d_i = (long long)(n >> d[p - 1]); p2.d_q = 1;
+            if (o.split_out) apply_split(p2, o, false);
             OK(launch_pass(d[p - 1], KIND_ROWT, p2, tpi * (long long)nb, st));
         }
         CU(cudaGetLastError());
@@ -769,8 +786,10 @@ static int exec_c2c(const cplx *src, cplx *dst, size_t n, size_t batch, size_t s
 // transform; dir < 0: applied to the INPUT of the inverse transform).  Rows of dst are in natural
 // k1 order.  n1 = 2^4 .. 2^20, cols a multiple of the tile width.  src != dst.
 // ------------------------------------------------------------------------------------------
-static int exec_cols(const cplx *src, cplx *dst, size_t n1, size_t cols, int dir, double scale, int lgM,
+static int exec_cols(const cplx *src, size_t src_ld, cplx *dst, size_t dst_ld, size_t n1, size_t cols, int dir, double scale, int lgM,
                      long long col_offset, cudaStream_t st) {
+    // src / dst are [n1][cols] blocks of row-major matrices with row pitches src_ld / dst_ld >= cols (a column chunk of a
+    // wider local matrix on one side, a dense exchange buffer on the other)
     OK(set_kernel_attrs());
     const int lg1 = ilog2(n1);
     const bool inv = dir < 0;
@@ -780,7 +799,7 @@ static int exec_cols(const cplx *src, cplx *dst, size_t n1, size_t cols, int dir
     for (int l : d) if (l < 4 || l > 10) return fail(NAPA_E_UNSUPPORTED, "column transform length 2^%d unsupported", lg1);
     for (int l : d) if (cols % ((size_t)1 << napa::plan_log2c(l))) return fail(NAPA_E_UNSUPPORTED, "cols must be a multiple of %d", 1 << napa::plan_log2c(l));
     BigTw gt{}; if (lgM > 0) OK(ensure_big_tw(lgM, &gt));
-    const long long B = (long long)cols;
+    const long long B = (long long)cols, SL = (long long)src_ld, DL = (long long)dst_ld;
     auto global_tw = [&](PassParams &p, long long mul_t, long long mul_a) {
         p.tw_lo = gt.lo; p.tw_hi = gt.hi; p.tw_shift = gt.shift; p.tw_mask = (1ull << lgM) - 1;
         p.tw_col_offset = col_offset; p.tw_col_shift = 0; p.tw_mul_t = mul_t; p.tw_mul_a = mul_a;
@@ -791,8 +810,8 @@ static int exec_cols(const cplx *src, cplx *dst, size_t n1, size_t cols, int dir
         const long long C = 1LL << napa::plan_log2c(l);
         PassParams p{};
         p.src = src; p.dst = dst; p.batch = 1; p.G = (int)(B / C); p.tiles_per_item = p.G;
-        p.s_SA = 0; p.s_SG = C; p.s_i = B; p.s_q = 1;
-        p.d_SA = 0; p.d_SG = C; p.d_i = B; p.d_q = 1;
+        p.s_SA = 0; p.s_SG = C; p.s_i = SL; p.s_q = 1;
+        p.d_SA = 0; p.d_SG = C; p.d_i = DL; p.d_q = 1;
         p.tw_mul_t = 1;
         if (inv) p.flags |= napa::PF_CONJ_IN | napa::PF_CONJ_OUT;
         if (scale != 1.0) { p.flags |= napa::PF_SCALE; p.scale = scale; }
@@ -805,43 +824,48 @@ static int exec_cols(const cplx *src, cplx *dst, size_t n1, size_t cols, int dir
     // Inverse (DIT, mirror): digit b first (input rows k1 = ka + La*kb), then digit a.
     const int la = d[0], lb = d[1];
     const long long La = 1LL << la, Lb = 1LL << lb;
-    cplx *scratch; OK(ensure_scratch(st, n1 * cols * sizeof(cplx), &scratch));
+    cplx *scratch; OK(ensure_scratch(st, n1 * cols * sizeof(cplx), &scratch));      // dense [n1][cols]
     BigTw it; OK(ensure_big_tw(lg1, &it));
     PassParams pa{}, pb{};
-    // digit a over the [La][Lb*B] view, intra twiddle W_n1^{ka * jb}, jb = col / B
+    // digit a: rows ia*Lb + jb, tile = (jb, C columns): outer index ra = jb, intra twiddle W_n1^{ka * jb}.  ld = pitch of the side
+    auto digit_a = [&](bool src_side, long long ld, long long &SA, long long &SG, long long &si, long long &sq) {
+        (void)src_side; SA = ld; SG = 1LL << napa::plan_log2c(la); si = Lb * ld; sq = 1;
+    };
     {
         const long long C = 1LL << napa::plan_log2c(la);
-        pa.batch = 1; pa.G = (int)((Lb * B) / C); pa.tiles_per_item = pa.G;
-        pa.s_SA = 0; pa.s_SG = C; pa.s_i = Lb * B; pa.s_q = 1;
-        pa.d_SA = 0; pa.d_SG = C; pa.d_i = Lb * B; pa.d_q = 1;
+        pa.batch = 1; pa.G = (int)(B / C); pa.tiles_per_item = (int)(Lb * (B / C));
         pa.tw_lo = it.lo; pa.tw_hi = it.hi; pa.tw_shift = it.shift; pa.tw_mask = (1ull << lg1) - 1;
-        pa.tw_mul_t = 1; pa.tw_mul_a = 0; pa.tw_col_offset = 0; pa.tw_col_shift = ilog2((size_t)B);
+        pa.tw_mul_t = 1; pa.tw_mul_a = 0; pa.tw_col_offset = 0; pa.tw_col_shift = 0; pa.tw_use_ra = 1;
     }
-    // digit b over the [La][Lb][B] view (A = La tiles rows), natural row order on the k1 side:
+    // digit b over the [La][Lb][.] view (outer index ra = ia / ka), natural row order on the k1 side:
     // position (ka, kb) <-> row ka + La*kb
     {
         const long long C = 1LL << napa::plan_log2c(lb);
         pb.batch = 1; pb.G = (int)(B / C); pb.tiles_per_item = (int)(La * (B / C));
-        pb.s_SA = Lb * B; pb.s_SG = C; pb.s_i = B; pb.s_q = 1;
-        pb.d_SA = Lb * B; pb.d_SG = C; pb.d_i = B; pb.d_q = 1;
         pb.tw_mul_t = 1;
     }
     if (!inv) {
         pa.src = src; pa.dst = scratch; pa.flags |= napa::PF_TW_STORE;
+        digit_a(true, SL, pa.s_SA, pa.s_SG, pa.s_i, pa.s_q);
+        digit_a(false, B, pa.d_SA, pa.d_SG, pa.d_i, pa.d_q);
         if (scale != 1.0) { pa.flags |= napa::PF_SCALE; pa.scale = scale; }
         pb.src = scratch; pb.dst = dst;
-        pb.d_SA = B; pb.d_i = La * B;                       // store row ka + La*kb
+        pb.s_SA = Lb * B; pb.s_SG = 1LL << napa::plan_log2c(lb); pb.s_i = B; pb.s_q = 1;
+        pb.d_SA = DL; pb.d_SG = pb.s_SG; pb.d_i = La * DL; pb.d_q = 1;          // store row ka + La*kb
         if (lgM > 0) global_tw(pb, La, 1);                   // k1 = ra + La*(t + m*T)
         OK(launch_pass(la, KIND_COL, pa, pa.tiles_per_item, st));
         OK(launch_pass(lb, KIND_COL, pb, pb.tiles_per_item, st));
     } else {
         // DIT mirror: first the b digit, reading rows k1 = ka + La*kb, global twiddle on its load
         pb.src = src; pb.dst = scratch;
-        pb.s_SA = B; pb.s_i = La * B;
+        pb.s_SA = SL; pb.s_SG = 1LL << napa::plan_log2c(lb); pb.s_i = La * SL; pb.s_q = 1;
+        pb.d_SA = Lb * B; pb.d_SG = pb.s_SG; pb.d_i = B; pb.d_q = 1;
         pb.flags |= napa::PF_CONJ_IN;
         if (scale != 1.0) { pb.flags |= napa::PF_SCALE; pb.scale = scale; }
         if (lgM > 0) global_tw(pb, La, 1);
         pa.src = scratch; pa.dst = dst; pa.flags |= napa::PF_TW_LOAD | napa::PF_CONJ_OUT;
+        digit_a(true, B, pa.s_SA, pa.s_SG, pa.s_i, pa.s_q);
+        digit_a(false, DL, pa.d_SA, pa.d_SG, pa.d_i, pa.d_q);
         OK(launch_pass(lb, KIND_COL, pb, pb.tiles_per_item, st));
         OK(launch_pass(la, KIND_COL, pa, pa.tiles_per_item, st));
     }
@@ -1189,7 +1213,7 @@ NAPA_API int napafft_init(int device) {
     // tunables: defaults first (a re-init after napafft_shutdown must not inherit the previous settings)
     { State d; G.chunk_bytes = d.chunk_bytes; G.zero_copy_bytes = d.zero_copy_bytes; G.max_scratch_bytes = d.max_scratch_bytes;
       G.fused_unit_bytes = d.fused_unit_bytes; G.fused_upg = d.fused_upg; G.fused_grid = d.fused_grid; G.use_fused = d.use_fused;
-      G.fused_prefetch = d.fused_prefetch; G.fused_tma = d.fused_tma; G.fused_lead = d.fused_lead; }
+      G.fused_prefetch = d.fused_prefetch; G.fused_tma = d.fused_tma; G.fused_lead = d.fused_lead; G.dist_chunks = d.dist_chunks; }
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_ZERO_COPY_KB")) G.zero_copy_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_MAX_SCRATCH_KB")) G.max_scratch_bytes = (size_t)atoll(env) << 10;
@@ -1200,6 +1224,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_FUSED_PREFETCH")) G.fused_prefetch = atoi(env);
     if (const char *env = getenv("NAPAFFT_FUSED_TMA")) G.fused_tma = atoi(env);
     if (const char *env = getenv("NAPAFFT_FUSED_LEAD")) G.fused_lead = atoi(env);
+    if (const char *env = getenv("NAPAFFT_DIST_CHUNKS")) G.dist_chunks = atoi(env);
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;
@@ -1362,7 +1387,7 @@ NAPA_API int napafft_c2c_cols_dev(const void *src, void *dst, size_t n1, size_t 
     if (dir != NAPA_FWD && dir != NAPA_INV) return fail(NAPA_E_BAD_ENUM, "direction %d is not 1 / -1", dir);
     OK(napafft_enter());
     std::lock_guard<std::mutex> lk(G.mu);
-    return exec_cols((const cplx *)src, (cplx *)dst, n1, cols, dir, scale, lg_twiddle_modulus, col_offset, (cudaStream_t)stream);
+    return exec_cols((const cplx *)src, cols, (cplx *)dst, cols, n1, cols, dir, scale, lg_twiddle_modulus, col_offset, (cudaStream_t)stream);
 }
 
 // dst[r][g][c] = src[g][r][c]   (g < groups, r < rows, c < cols): re-layout around the all-to-all
@@ -1415,6 +1440,292 @@ NAPA_API int napafft_host_unregister(void *ptr) {
     if (!ptr) return fail(NAPA_E_NULL, "NULL pointer");
     CU(cudaHostUnregister(ptr));
     return NAPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Distributed four-step: ONE transform of N = 2^lgN points over P processes, one GPU each (BASELINE config 5,
+// SURVEY.md 8e).  N = N1 * N2 (N1 = 2^(lgN/2)); x[j1*N2 + j2] is an [N1][N2] matrix.
+//   time layout (rank g):  columns j2 in [g*B, (g+1)*B), B = N2/P, a local [N1][B] array;
+//   freq layout (rank h):  rows k1 in [h*R, (h+1)*R), R = N1/P, of X[k1 + N1*k2], a local [R][N2] array.
+// forward:  the B local columns are cut into `nch` chunks of Bc columns.  Chunk c: column FFTs over j1 with
+//           W_N^{j2 k1} fused into their last pass write the dense block send_c = [N1][Bc], whose P slabs of R rows
+//           are the messages -- no packing; the all-to-all of chunk c (ncclSend/ncclRecv on the library's
+//           communication stream) then overlaps the column FFTs of chunk c + 1.  The rows of the received
+//           [chunk][rank][R][Bc] pieces are transformed in place of any re-layout pass: the first row pass reads
+//           them through split_offset().
+// inverse:  the mirror image (row pass stores into the exchange layout, chunked exchange, twiddled column passes
+//           writing the caller's [N1][B] array), scaled by 1/N.
+// The exchange itself is a callback so that hosts that own their communicator (Python + torch.distributed in the
+// tests) can drive the same pipeline through napafft_dist_cols_dev / napafft_dist_rows_dev.
+// ------------------------------------------------------------------------------------------
+struct DistGeom { int lgN, lg1, lg2, P, nch; size_t N1, N2, B, R, Bc; };
+static int dist_geom(int lgN, int P, int nch, DistGeom *g) {
+    if (lgN < 8 || lgN > 40) return fail(NAPA_E_UNSUPPORTED, "distributed transform of 2^%d points unsupported", lgN);
+    if (P < 1 || !pow2((size_t)P)) return fail(NAPA_E_UNSUPPORTED, "the number of ranks (%d) must be a power of two", P);
+    g->lgN = lgN; g->lg1 = lgN / 2; g->lg2 = lgN - g->lg1; g->P = P;
+    g->N1 = (size_t)1 << g->lg1; g->N2 = (size_t)1 << g->lg2;
+    if (g->N1 % P || g->N2 % P) return fail(NAPA_E_UNSUPPORTED, "%d ranks do not divide 2^%d x 2^%d", P, g->lg1, g->lg2);
+    g->B = g->N2 / P; g->R = g->N1 / P;
+    // a chunk holds whole tiles of every pass that touches it (a tile spans at most 128 adjacent columns / points)
+    const size_t min_bc = 128;
+    if (nch <= 0) nch = 4;
+    while (nch > 1 && (g->B % nch || g->B / nch < min_bc)) nch >>= 1;
+    if (g->B < min_bc) return fail(NAPA_E_UNSUPPORTED, "fewer than %zu columns per rank (2^%d points over %d ranks)", min_bc, lgN, P);
+    if (!pow2((size_t)nch)) return fail(NAPA_E_UNSUPPORTED, "the number of chunks must be a power of two");
+    g->nch = nch; g->Bc = g->B / nch;
+    return NAPA_OK;
+}
+
+// column stage of chunk c.  forward: x_local [N1][B] -> xbuf chunk c; inverse: xbuf chunk c -> x_local
+static int dist_cols(const DistGeom &g, int rank, int c, int dir, cplx *x_local, cplx *xbuf, cudaStream_t st) {
+    cplx *chunk = xbuf + (size_t)c * g.N1 * g.Bc;
+    const long long col0 = (long long)rank * (long long)g.B + (long long)c * (long long)g.Bc;
+    if (dir > 0) return exec_cols(x_local + (size_t)c * g.Bc, g.B, chunk, g.Bc, g.N1, g.Bc, +1, 1.0, g.lgN, col0, st);
+    return exec_cols(chunk, g.Bc, x_local + (size_t)c * g.Bc, g.B, g.N1, g.Bc, -1, 1.0 / (double)((size_t)1 << g.lgN), g.lgN, col0, st);
+}
+// row stage.  forward: exchange layout -> X_local [R][N2]; inverse: X_local -> exchange layout (unscaled)
+static int dist_rows(const DistGeom &g, int dir, cplx *xbuf, cplx *X_local, cudaStream_t st) {
+    C2COpts o{};
+    o.dir = dir; o.in_order = 1; o.scale = 1.0;
+    o.sp_lgbc = ilog2(g.Bc); o.sp_lgnch = ilog2((size_t)g.nch);
+    o.sp_chunk_stride = (long long)(g.N1 * g.Bc); o.sp_rank_stride = (long long)(g.R * g.Bc);
+    if (dir > 0) { o.split_in = true; return exec_c2c(xbuf, X_local, g.N2, g.R, g.Bc, g.N2, o, st); }
+    o.split_out = true;
+    return exec_c2c(X_local, xbuf, g.N2, g.R, g.N2, g.Bc, o, st);
+}
+
+#ifndef NAPA_EMULATE
+// NCCL is bound at run time (dlopen by SONAME: a process that already carries libnccl.so.2, e.g. through PyTorch,
+// shares that copy), so the library itself has no link-time dependency on it.
+#include <dlfcn.h>
+#include <nccl.h>
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi NC;
+static int nccl_load() {
+    if (NC.lib) return NAPA_OK;
+    const char *names[] = { getenv("NAPAFFT_NCCL_LIBRARY"), "libnccl.so.2", "libnccl.so" };
+    for (const char *nm : names) { if (nm && (NC.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break; }
+    if (!NC.lib) return fail(NAPA_E_NCCL, "libnccl.so.2 not found (%s); set NAPAFFT_NCCL_LIBRARY", dlerror());
+#define NAPA_NCCL_SYM(field, sym) do { *(void **)(&NC.field) = dlsym(NC.lib, sym); if (!NC.field) { NC.lib = nullptr; return fail(NAPA_E_NCCL, "%s missing from the NCCL library", sym); } } while (0)
+    NAPA_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NAPA_NCCL_SYM(CommInitRank, "ncclCommInitRank"); NAPA_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    NAPA_NCCL_SYM(GroupStart, "ncclGroupStart"); NAPA_NCCL_SYM(GroupEnd, "ncclGroupEnd"); NAPA_NCCL_SYM(Send, "ncclSend"); NAPA_NCCL_SYM(Recv, "ncclRecv");
+    NAPA_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NAPA_NCCL_SYM
+    return NAPA_OK;
+}
+#define NCCL(call)                                                                                  \
+    do {                                                                                            \
+        ncclResult_t r_ = (call);                                                                   \
+        if (r_ != ncclSuccess) return fail(NAPA_E_NCCL, "%s failed: %s", #call, NC.GetErrorString(r_)); \
+    } while (0)
+#endif
+
+struct DistState {
+    int rank = 0, nranks = 0;                    // 0 ranks = not initialised
+#ifndef NAPA_EMULATE
+    ncclComm_t comm = nullptr;
+#endif
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ready[16] = {}, ev_done[16] = {};
+    cplx *send = nullptr, *recv = nullptr; size_t buf_elems = 0;
+};
+static DistState D;
+
+static int dist_buffers(size_t elems) {
+    if (D.buf_elems >= elems) return NAPA_OK;
+    CU(cudaDeviceSynchronize());
+    if (D.send) CU(cudaFree(D.send));
+    if (D.recv) CU(cudaFree(D.recv));
+    D.send = D.recv = nullptr; D.buf_elems = 0;
+    CU(cudaMalloc((void **)&D.send, elems * sizeof(cplx)));
+    CU(cudaMalloc((void **)&D.recv, elems * sizeof(cplx)));
+    D.buf_elems = elems;
+    return NAPA_OK;
+}
+static int dist_events() {
+    if (D.comm_stream) return NAPA_OK;
+    CU(cudaStreamCreateWithFlags(&D.comm_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) {
+        CU(cudaEventCreateWithFlags(&D.ev_ready[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&D.ev_done[i], cudaEventDisableTiming));
+    }
+    return NAPA_OK;
+}
+// all-to-all of chunk c on the communication stream: slab h of `from` goes to rank h, slab g of `to` comes from rank g
+static int dist_exchange_chunk(const DistGeom &g, int c, const cplx *from, cplx *to) {
+    const size_t slab = g.R * g.Bc, off = (size_t)c * g.N1 * g.Bc;
+    if (g.P == 1) {
+        CU(cudaMemcpyAsync(to + off, from + off, slab * sizeof(cplx), cudaMemcpyDeviceToDevice, D.comm_stream));
+        return NAPA_OK;
+    }
+#ifdef NAPA_EMULATE
+    return fail(NAPA_E_NCCL, "no NCCL in the emulation build");
+#else
+    NCCL(NC.GroupStart());
+    for (int h = 0; h < g.P; h++) {
+        NCCL(NC.Send(from + off + (size_t)h * slab, 2 * slab, ncclDouble, h, D.comm, D.comm_stream));
+        NCCL(NC.Recv(to + off + (size_t)h * slab, 2 * slab, ncclDouble, h, D.comm, D.comm_stream));
+    }
+    NCCL(NC.GroupEnd());
+    return NAPA_OK;
+#endif
+}
+
+static int exec_dist(cplx *src_local, cplx *dst_local, int lgN, int dir, int nch, cudaStream_t st) {
+    DistGeom g;
+    OK(dist_geom(lgN, std::max(D.nranks, 1), nch, &g));
+    if (g.nch > 16) return fail(NAPA_E_UNSUPPORTED, "at most 16 chunks");
+    OK(dist_events());
+    OK(dist_buffers(g.N1 * g.B));
+    if (dir > 0) {
+        for (int c = 0; c < g.nch; c++) {
+            OK(dist_cols(g, D.rank, c, +1, src_local, D.send, st));
+            CU(cudaEventRecord(D.ev_ready[c], st));
+            CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[c], 0));
+            OK(dist_exchange_chunk(g, c, D.send, D.recv));
+        }
+        CU(cudaEventRecord(D.ev_done[0], D.comm_stream));
+        CU(cudaStreamWaitEvent(st, D.ev_done[0], 0));
+        OK(dist_rows(g, +1, D.recv, dst_local, st));
+    } else {
+        OK(dist_rows(g, -1, D.send, src_local, st));
+        CU(cudaEventRecord(D.ev_ready[0], st));
+        CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[0], 0));
+        for (int c = 0; c < g.nch; c++) {
+            OK(dist_exchange_chunk(g, c, D.send, D.recv));
+            CU(cudaEventRecord(D.ev_done[c], D.comm_stream));
+            CU(cudaStreamWaitEvent(st, D.ev_done[c], 0));
+            OK(dist_cols(g, D.rank, c, -1, dst_local, D.recv, st));
+        }
+    }
+    // the buffers are reused by the next call: keep the communication stream behind this call's compute
+    CU(cudaEventRecord(D.ev_ready[15], st));
+    CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[15], 0));
+    return NAPA_OK;
+}
+
+NAPA_API int napafft_dist_unique_id(void *out128) {
+    if (!out128) return fail(NAPA_E_NULL, "out must not be NULL");
+#ifdef NAPA_EMULATE
+    memset(out128, 0, 128);
+    return NAPA_OK;
+#else
+    OK(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NCCL(NC.GetUniqueId((ncclUniqueId *)out128));
+    return NAPA_OK;
+#endif
+}
+NAPA_API int napafft_dist_init(const void *unique_id128, int rank, int nranks) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(NAPA_E_BAD_ENUM, "rank %d of %d", rank, nranks);
+    if (!pow2((size_t)nranks)) return fail(NAPA_E_UNSUPPORTED, "the number of ranks (%d) must be a power of two", nranks);
+    OK(napafft_enter());
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (D.nranks) return fail(NAPA_E_UNSUPPORTED, "the distributed context is already initialised (napafft_dist_shutdown first)");
+    if (nranks > 1) {
+#ifdef NAPA_EMULATE
+        return fail(NAPA_E_NCCL, "no NCCL in the emulation build");
+#else
+        if (!unique_id128) return fail(NAPA_E_NULL, "unique id must not be NULL");
+        OK(nccl_load());
+        ncclUniqueId id;
+        memcpy(&id, unique_id128, sizeof id);
+        NCCL(NC.CommInitRank(&D.comm, nranks, id, rank));
+#endif
+    }
+    D.rank = rank; D.nranks = nranks;
+    return NAPA_OK;
+}
+static void dist_release() {
+#ifndef NAPA_EMULATE
+    if (D.comm) { NC.CommDestroy(D.comm); D.comm = nullptr; }
+#endif
+    if (D.send) cudaFree(D.send);
+    if (D.recv) cudaFree(D.recv);
+    if (D.comm_stream) {
+        cudaStreamDestroy(D.comm_stream);
+        for (int i = 0; i < 16; i++) { cudaEventDestroy(D.ev_ready[i]); cudaEventDestroy(D.ev_done[i]); }
+    }
+    D = DistState();
+}
+NAPA_API int napafft_dist_shutdown(void) {
+    if (!G.inited.load()) return NAPA_OK;
+    OK(napafft_enter());
+    std::lock_guard<std::mutex> lk(G.mu);
+    cudaDeviceSynchronize();
+    dist_release();
+    return NAPA_OK;
+}
+static int check_dist_args(const void *a, const void *b, int dir) {
+    if (!a || !b) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (a == b) return fail(NAPA_E_UNSUPPORTED, "the distributed transform is out of place");
+    if (dir != NAPA_FWD && dir != NAPA_INV) return fail(NAPA_E_BAD_ENUM, "direction %d is not 1 / -1", dir);
+    if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(NAPA_E_UNSUPPORTED, "device pointers must be 16-byte aligned");
+    return NAPA_OK;
+}
+NAPA_API int napafft_dist_c2c_dev(const void *src_local, void *dst_local, int lgN, int dir, void *stream) {
+    OK(check_dist_args(src_local, dst_local, dir));
+    OK(napafft_enter());
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!D.nranks) return fail(NAPA_E_NCCL, "napafft_dist_init has not been called");
+    return exec_dist((cplx *)src_local, (cplx *)dst_local, lgN, dir, G.dist_chunks, (cudaStream_t)stream);
+}
+NAPA_API int napafft_dist_c2c(const double *src_local, double *dst_local, int lgN, int dir) {
+    if (!src_local || !dst_local) return fail(NAPA_E_NULL, "src/dst must not be NULL");
+    if (dir != NAPA_FWD && dir != NAPA_INV) return fail(NAPA_E_BAD_ENUM, "direction %d is not 1 / -1", dir);
+    OK(napafft_enter());
+    if (!D.nranks) return fail(NAPA_E_NCCL, "napafft_dist_init has not been called");
+    if (lgN < 8 || lgN > 40) return fail(NAPA_E_UNSUPPORTED, "distributed transform of 2^%d points unsupported", lgN);
+    const size_t bytes = (((size_t)1 << lgN) / (size_t)D.nranks) * sizeof(cplx);
+    OK(ensure_staging(0));
+    cudaStream_t st = staging().stream[0];
+    void *d_in = nullptr, *d_out = nullptr;
+    int rc = NAPA_OK;
+    auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == NAPA_OK) rc = fail(NAPA_E_CUDA, "%s", cudaGetErrorString(e)); return e == cudaSuccess; };
+    if (cu(cudaMalloc(&d_in, bytes)) && cu(cudaMalloc(&d_out, bytes))) {
+        cu(cudaMemcpyAsync(d_in, src_local, bytes, cudaMemcpyHostToDevice, st));
+        if (rc == NAPA_OK) rc = LOCKED(exec_dist((cplx *)d_in, (cplx *)d_out, lgN, dir, G.dist_chunks, st));
+        if (rc == NAPA_OK) cu(cudaMemcpyAsync(dst_local, d_out, bytes, cudaMemcpyDeviceToHost, st));
+        cu(cudaStreamSynchronize(st));
+    }
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+NAPA_API int napafft_dist_geometry(int lgN, int nranks, size_t *n1, size_t *n2, size_t *cols_per_rank, size_t *rows_per_rank, int *nchunks) {
+    OK(napafft_enter());
+    DistGeom g;
+    OK(dist_geom(lgN, nranks, LOCKED(G.dist_chunks), &g));
+    if (n1) *n1 = g.N1; if (n2) *n2 = g.N2; if (cols_per_rank) *cols_per_rank = g.B; if (rows_per_rank) *rows_per_rank = g.R;
+    if (nchunks) *nchunks = g.nch;
+    return NAPA_OK;
+}
+// the two local stages for hosts that carry the exchange themselves: xbuf is the [nch][N1][Bc] exchange buffer
+NAPA_API int napafft_dist_cols_dev(void *x_local, void *xbuf, int lgN, int nranks, int rank, int chunk, int dir, void *stream) {
+    OK(check_dist_args(x_local, xbuf, dir));
+    OK(napafft_enter());
+    std::lock_guard<std::mutex> lk(G.mu);
+    DistGeom g;
+    OK(dist_geom(lgN, nranks, G.dist_chunks, &g));
+    if (rank < 0 || rank >= nranks || chunk < 0 || chunk >= g.nch) return fail(NAPA_E_BAD_ENUM, "rank %d / chunk %d out of range", rank, chunk);
+    return dist_cols(g, rank, chunk, dir, (cplx *)x_local, (cplx *)xbuf, (cudaStream_t)stream);
+}
+NAPA_API int napafft_dist_rows_dev(void *xbuf, void *X_local, int lgN, int nranks, int dir, void *stream) {
+    OK(check_dist_args(xbuf, X_local, dir));
+    OK(napafft_enter());
+    std::lock_guard<std::mutex> lk(G.mu);
+    DistGeom g;
+    OK(dist_geom(lgN, nranks, G.dist_chunks, &g));
+    return dist_rows(g, dir, (cplx *)xbuf, (cplx *)X_local, (cudaStream_t)stream);
 }
 
 // ---- host-pointer entry points ----

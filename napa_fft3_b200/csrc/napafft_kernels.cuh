@@ -169,6 +169,8 @@ enum : unsigned {
     PF_RFFT_POST  = 1u << 12,  // single-pass row tiles: rfft epilogue (real.lisp:16-30, 128-134) fused into the store
     PF_ZIP2       = 1u << 13,  // %2rfft: the input is two REAL vectors, z = src[.] + i src_im[.] (strides in doubles)
     PF_SPLIT2_POST = 1u << 14, // %2rfft: single-pass row tiles store the two spectra E (at i) and O (at L + i), real.lisp:16-30
+    PF_SPLIT_IN   = 1u << 15,  // distributed four-step: the item is read from the exchange layout [chunk][rank][row][Bc] (split_offset)
+    PF_SPLIT_OUT  = 1u << 16,  // ... or written to it
 };
 
 struct PassParams {
@@ -198,7 +200,19 @@ struct PassParams {
     const cplx *r2tw;                               // reference recurrence table (rifft pre-pass)
     long long aux_off;                              // N for PF_RIFFT_PRE
     const double *src_im;                           // PF_ZIP2: the second real input
+    // PF_SPLIT_IN / PF_SPLIT_OUT: in-row index j -> j % Bc + ((j / Bc) % nch) * sp_chunk_stride + (j / (Bc * nch)) * sp_rank_stride
+    int sp_lgbc, sp_lgnch;
+    long long sp_chunk_stride, sp_rank_stride;
+    int tw_use_ra;                                  // inter-pass twiddle: the column factor is the tile's outer index ra, not its column
 };
+// Row j of a distributed transform lives in P * nch pieces of Bc points (one per source rank and column chunk,
+// exactly as the all-to-all delivered them): logical in-row index -> element offset inside the item.
+__device__ __forceinline__ long long split_offset(const PassParams &p, const long long j) {
+    const long long lo = j & ((1LL << p.sp_lgbc) - 1);
+    const long long ch = (j >> p.sp_lgbc) & ((1LL << p.sp_lgnch) - 1);
+    const long long rk = j >> (p.sp_lgbc + p.sp_lgnch);
+    return lo + ch * p.sp_chunk_stride + rk * p.sp_rank_stride;
+}
 
 __device__ __forceinline__ cplx ldg_c(const cplx *p) { return __ldg(p); }
 // Data-path loads/stores carry an L2 eviction hint (HINT_*): streaming operands (user src / dst,
@@ -505,8 +519,8 @@ struct Stages {
 // 18 complex products instead of 32 dependent table look-ups; every seed load is issued at once.
 template <int T>
 __device__ __forceinline__ void apply_big_twiddle(cplx (&v)[16], const PassParams &p, int t, unsigned col, int ra) {
-    const unsigned long long colx = (unsigned long long)(p.tw_col_offset + (long long)(col >> p.tw_col_shift)) & p.tw_mask;
-    const unsigned long long idx = ((unsigned long long)(p.tw_mul_a * ra + p.tw_mul_t * t)) & p.tw_mask;
+    const unsigned long long colx = (unsigned long long)(p.tw_col_offset + (p.tw_use_ra ? (long long)ra : (long long)(col >> p.tw_col_shift))) & p.tw_mask;
+    const unsigned long long idx = ((unsigned long long)(p.tw_use_ra ? p.tw_mul_t * t : p.tw_mul_a * ra + p.tw_mul_t * t)) & p.tw_mask;
     const unsigned long long eb = (idx * colx) & p.tw_mask;
     const unsigned long long ed = ((((unsigned long long)(p.tw_mul_t * T)) & p.tw_mask) * colx) & p.tw_mask;
     const unsigned long long lomask = (1ull << p.tw_shift) - 1;
@@ -677,6 +691,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         } else if ((flags & PF_IN_REV) && !in_reorder) {
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(src + (long long)rev_bits(t + m * T, LOG2L) * s_i, src_hint, pol);
+        } else if (flags & PF_SPLIT_IN) {
+            const cplx *item0 = p.src + (c.item + src_item_delta) * p.src_batch_stride;
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = ld_data<COHERENT>(item0 + split_offset(p, s_xoff + (long long)(t + m * T) * s_i), src_hint, pol);
         } else {
             const cplx *s0 = src + (long long)t * s_i;
             const long long step = (long long)T * s_i;
@@ -837,6 +855,10 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         if ((flags & PF_OUT_REV) && !out_reorder) {
 #pragma unroll
             for (int m = 0; m < 16; m++) st_data(dst + (long long)rev_bits(d.t + m * T, LOG2L) * d_i, v[m], dst_hint, pol);
+        } else if (flags & PF_SPLIT_OUT) {
+            cplx *item0 = p.dst + (d.item + dst_item_delta) * p.dst_batch_stride;
+#pragma unroll
+            for (int m = 0; m < 16; m++) st_data(item0 + split_offset(p, d.d_xoff + (long long)(d.t + m * T) * d_i), v[m], dst_hint, pol);
         } else {
             cplx *d0 = dst + (long long)d.t * d_i;
             const long long step = (long long)T * d_i;

@@ -43,41 +43,63 @@ def max_over_ranks(value: float, dist=None, device=None) -> float:
     return float(t.item())
 
 
+_native_ctx = None          # (rank, nranks) of the library-owned communicator of this process
+
+
 class DistributedFFT:
     """One complex-double transform of N = 2^lgN points spread over the P ranks of a
     torch.distributed group (BASELINE config C5): the four-step N = N1*N2 with ONE
-    all-to-all.
+    all-to-all, cut into column chunks so that the exchange of a chunk overlaps the column FFTs of the next.
 
-    Layouts (both are "column blocks of a row-major matrix"; no rank ever holds the whole vector):
+    Layouts (both are "blocks of a row-major matrix"; no rank ever holds the whole vector):
       time  side: x[j1*N2 + j2] viewed as [N1][N2];  rank g holds columns j2 in [g*B, (g+1)*B),
                   B = N2/P, as a contiguous local [N1][B] array;
       freq  side: X[k1 + N1*k2] viewed as [N1][N2] (k1 = row); rank h holds rows k1 in
                   [h*R, (h+1)*R), R = N1/P, as a contiguous local [R][N2] array (k2 natural).
-    forward():  local column FFTs over j1 with the twiddle W_N^{j2 k1} fused into the last column
-                pass -> all-to-all of contiguous [R][B] slabs -> re-layout -> local row FFTs over j2.
-    inverse():  the same steps backwards (unscaled row inverse, exchange, twiddled column inverse
-                with the 1/N scale fused into its first load).
-    Device work goes through the C ABI (napafft_c2c_cols_dev / napafft_relayout_dev /
-    napafft_c2c_dev); torch.distributed (NCCL over NVLink, or gloo on CPU in the tests) carries the
-    exchange.
+    forward():  chunk by chunk, local column FFTs over j1 with the twiddle W_N^{j2 k1} fused into the last
+                column pass -> all-to-all of contiguous [R][Bc] slabs; then local row FFTs over j2 that read
+                the received pieces in place (no re-layout pass).
+    inverse():  the same steps backwards, scaled by 1/N.
+
+    Two ways to carry the exchange:
+      native (default on CUDA): the C library owns an NCCL communicator (napafft_dist_init; the unique id is
+        broadcast once through torch.distributed) and napafft_dist_c2c_dev runs the whole pipeline, the
+        exchange on its own stream;
+      host-carried (gloo / CPU tests, or native=False): torch.distributed.all_to_all_single per chunk between the
+        library's two local stages napafft_dist_cols_dev / napafft_dist_rows_dev.
     """
 
-    def __init__(self, lgN, binding, dist, device, stream=None):
+    def __init__(self, lgN, binding, dist, device, stream=None, native=None):
+        import ctypes as C
         import torch
+        global _native_ctx
         self.torch, self.b, self.dist, self.device = torch, binding, dist, device
         self.P = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.P > 1 else 0
         self.lgN = lgN
-        self.lg1 = lgN // 2
-        self.N1, self.N2 = 1 << self.lg1, 1 << (lgN - self.lg1)
-        if self.N1 % self.P or self.N2 % self.P:
-            raise ValueError("P must divide both N1 and N2")
-        self.B, self.R = self.N2 // self.P, self.N1 // self.P
+        n1, n2, B, R, nch = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int()
+        binding.dist_geometry(lgN, self.P, C.byref(n1), C.byref(n2), C.byref(B), C.byref(R), C.byref(nch))
+        self.N1, self.N2, self.B, self.R, self.nch = n1.value, n2.value, B.value, R.value, nch.value
+        self.Bc = self.B // self.nch
         self._stream = stream
-        mk = lambda *shape: torch.empty(shape, dtype=torch.complex128, device=device)
-        self.send = mk(self.N1, self.B)
-        self.recv = mk(self.N1, self.B)
-        self.rows = mk(self.R, self.N2)
+        self.native = (device.type == "cuda" or self.P == 1) if native is None else bool(native)
+        if self.native:
+            if _native_ctx is None:
+                uid = (C.c_ubyte * 128)()
+                if self.P > 1:
+                    if self.rank == 0:
+                        binding.dist_unique_id(uid)
+                    box = [bytes(uid)]
+                    dist.broadcast_object_list(box, src=0)
+                    uid = (C.c_ubyte * 128).from_buffer_copy(box[0])
+                binding.dist_init(uid, self.rank, self.P)
+                _native_ctx = (self.rank, self.P)
+            elif _native_ctx != (self.rank, self.P):
+                raise ValueError("this process already owns a communicator of another shape")
+        else:
+            mk = lambda *shape: torch.empty(shape, dtype=torch.complex128, device=device)
+            self.xs = mk(self.nch, self.N1, self.Bc)
+            self.xr = mk(self.nch, self.N1, self.Bc)
 
     def _st(self):
         if self._stream is not None:
@@ -99,11 +121,13 @@ class DistributedFFT:
         assert x_local.shape == (self.N1, self.B) and x_local.dtype == t.complex128 and x_local.is_contiguous()
         out = t.empty((self.R, self.N2), dtype=t.complex128, device=self.device) if out is None else out
         st = self._st()
-        self.b.c2c_cols_dev(x_local.data_ptr(), self.send.data_ptr(), self.N1, self.B, 1, 1.0, self.lgN,
-                            self.rank * self.B, st)
-        self._exchange(self.recv, self.send)                       # recv = [P][R][B]
-        self.b.relayout_dev(self.recv.data_ptr(), self.rows.data_ptr(), self.P, self.R, self.B, 0, st)   # -> [R][P][B]
-        self.b.c2c_dev(self.rows.data_ptr(), out.data_ptr(), self.N2, self.R, self.N2, 1, 0, 1, None, 0, 0, st)
+        if self.native:
+            self.b.dist_c2c_dev(x_local.data_ptr(), out.data_ptr(), self.lgN, 1, st)
+            return out
+        for c in range(self.nch):
+            self.b.dist_cols_dev(x_local.data_ptr(), self.xs.data_ptr(), self.lgN, self.P, self.rank, c, 1, st)
+            self._exchange(self.xr[c], self.xs[c])
+        self.b.dist_rows_dev(self.xr.data_ptr(), out.data_ptr(), self.lgN, self.P, 1, st)
         return out
 
     def inverse(self, X_local, out=None):
@@ -112,12 +136,23 @@ class DistributedFFT:
         assert X_local.shape == (self.R, self.N2) and X_local.dtype == t.complex128 and X_local.is_contiguous()
         out = t.empty((self.N1, self.B), dtype=t.complex128, device=self.device) if out is None else out
         st = self._st()
-        self.b.c2c_dev(X_local.data_ptr(), self.rows.data_ptr(), self.N2, self.R, self.N2, -1, 0, 1, None, 0, 0, st)
-        self.b.relayout_dev(self.rows.data_ptr(), self.send.data_ptr(), self.P, self.R, self.B, 1, st)   # -> [P][R][B]
-        self._exchange(self.recv, self.send)                       # recv = [N1][B], rows k1 natural
-        self.b.c2c_cols_dev(self.recv.data_ptr(), out.data_ptr(), self.N1, self.B, -1, 1.0 / float(1 << self.lgN),
-                            self.lgN, self.rank * self.B, st)
+        if self.native:
+            self.b.dist_c2c_dev(X_local.data_ptr(), out.data_ptr(), self.lgN, -1, st)
+            return out
+        self.b.dist_rows_dev(self.xs.data_ptr(), X_local.data_ptr(), self.lgN, self.P, -1, st)
+        for c in range(self.nch):
+            self._exchange(self.xr[c], self.xs[c])
+            self.b.dist_cols_dev(out.data_ptr(), self.xr.data_ptr(), self.lgN, self.P, self.rank, c, -1, st)
         return out
+
+    def exchange_only(self, steps=1):
+        """the all-to-all alone on buffers of the transform's size (bench: NVLink roofline of the exchange)"""
+        t = self.torch
+        if not hasattr(self, "_xa"):
+            self._xa = t.zeros((self.N1, self.B), dtype=t.complex128, device=self.device)
+            self._xb = t.empty_like(self._xa)
+        for _ in range(steps):
+            self._exchange(self._xb, self._xa)
 
     # helpers for tests / host callers: cut a full host vector into this rank's local arrays
     def scatter_time(self, x_full):

@@ -137,10 +137,30 @@ def gaussian(sigma):
     return _gaussian_cache[sigma]
 
 
+def _expt(base, power):
+    """CL EXPT as SBCL evaluates it for a float base: an integer power goes through INTEXP (repeated squaring in the
+    base's own precision, one rounding per multiplication -- not a correctly rounded pow); a float power is computed
+    in double precision and rounded to single when both arguments are single."""
+    if isinstance(power, (int, np.integer)) and not isinstance(power, bool):
+        p = abs(int(power))
+        total = base if p & 1 else type(base)(1)
+        p >>= 1
+        while p:
+            base = base * base
+            if p & 1:
+                total = base * total
+            p >>= 1
+        return total if power >= 0 else type(base)(1) / total
+    r = math.pow(float(base), float(power)) if base >= 0 else complex(float(base)) ** float(power)
+    if isinstance(base, np.float32) and isinstance(power, np.float32) and not isinstance(r, complex):
+        return _f32(r)
+    return r
+
+
 def gaussian_bartlett_x(sigma, triangle_exponent):
     key = (sigma, triangle_exponent)
     if key not in _gb_cache:
-        _gb_cache[key] = lambda i, n: np.real(bartlett(i, n) ** triangle_exponent) * gauss_star(sigma, i, n)
+        _gb_cache[key] = lambda i, n: np.real(_expt(bartlett(i, n), triangle_exponent)) * gauss_star(sigma, i, n)
     return _gb_cache[key]
 
 

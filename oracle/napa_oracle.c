@@ -443,6 +443,30 @@ NAPA_ORACLE_API double napa_oracle_window_fn(int id, long i, long n, double p0) 
     return NAN;
 }
 
+/* windowing.lisp:43-45 cosine-series with caller-supplied coefficients (all arithmetic in double: PI is a
+ * double, so (* scale (cos ...)) is double whatever the coefficient's float type) */
+NAPA_ORACLE_API double napa_oracle_cosine_series(long i, long n, double a0, double a1, double a2, double a3) {
+    const double pi = 3.141592653589793;
+    double f1 = a1 * cos(((2.0 * pi) * (double)i) / (double)(n - 1));
+    double f2 = a2 * cos(((4.0 * pi) * (double)i) / (double)(n - 1));
+    double f3 = a3 * cos(((6.0 * pi) * (double)i) / (double)(n - 1));
+    return ((a0 + (-f1)) + f2) + (-f3);
+}
+
+/* windowing.lisp:36-41 gaussian*bartlett^x for a single-float sigma and a non-negative INTEGER exponent:
+ * (expt single integer) is SBCL's INTEXP, repeated squaring in single precision; the product with gauss*
+ * (single) is single; window-vector then widens it */
+NAPA_ORACLE_API double napa_oracle_gaussian_bartlett_x(long i, long n, double sigma, long power) {
+    float base = (float)napa_oracle_window_fn(4, i, n, 0.0);
+    float total = (power & 1) ? base : 1.0f;
+    for (long nextn = power >> 1; nextn != 0; nextn >>= 1) {
+        base = base * base;
+        if (nextn & 1) total = base * total;
+    }
+    float g = (float)napa_oracle_window_fn(7, i, n, sigma);
+    return (double)(total * g);
+}
+
 /* windowing.lisp:53-65 window-vector (the cache is the caller's business) */
 NAPA_ORACLE_API int napa_oracle_window_vector(int id, size_t n, double p0, int bit_reverse, double *out) {
     for (size_t i = 0; i < n; i++) out[i] = napa_oracle_window_fn(id, (long)i, (long)n, p0);

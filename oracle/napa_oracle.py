@@ -229,6 +229,22 @@ def window_fn(name, i, n, param=0.0):
     return lib().napa_oracle_window_fn(WINDOW_IDS[name], i, n, float(param))
 
 
+def cosine_series(i, n, a0, a1, a2, a3):
+    """windowing.lisp:43-45"""
+    f = lib().napa_oracle_cosine_series
+    f.restype = C.c_double
+    f.argtypes = [C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double]
+    return f(i, n, float(a0), float(a1), float(a2), float(a3))
+
+
+def gaussian_bartlett_x(i, n, sigma, power):
+    """windowing.lisp:36-41, single-float sigma, integer exponent"""
+    f = lib().napa_oracle_gaussian_bartlett_x
+    f.restype = C.c_double
+    f.argtypes = [C.c_long, C.c_long, C.c_double, C.c_long]
+    return f(i, n, float(sigma), int(power))
+
+
 def window_vector(name, n, bit_reverse=False, param=0.0):
     """windowing.lisp:53-65"""
     out = np.zeros(n, dtype=np.float64)

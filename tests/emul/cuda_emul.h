@@ -113,6 +113,7 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }

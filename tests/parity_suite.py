@@ -242,6 +242,31 @@ def check_windowed(napa, n=64):
     assert nre(napa.windowed_rifft(spec.copy()), O.windowed_rifft(spec.copy())) <= tol(n)
 
 
+def check_get_windowed_fft(napa, n):
+    import pytest
+    """interface.lisp:191-217 get-windowed-fft: closures (vec window) for every direction / order / window type,
+    default scales (nil forward, :inv inverse), against the oracle's fft / ifft with the same window"""
+    wr, wc = rand_r(31, n, 0.5, 1.5), rand_c(32, n)
+    for forward in (True, False):
+        for in_order in (True, False):
+            for wtype, w in (("real-sample", wr), ("complex-sample", wc)):
+                fun = napa.get_windowed_fft(n, wtype, forward=forward, in_order=in_order)
+                x = rand_c(33 + n, n)
+                got = fun(x.copy(), w)
+                if forward:
+                    want = O.fft(x.copy(), in_order=in_order, window=w)
+                else:
+                    want = O.ifft(x.copy(), in_order=in_order, scale="inv", window=w)
+                assert nre(got, want) <= tol(n), (n, forward, in_order, wtype)
+    # explicit scale, and the result is the argument itself (in place)
+    fun = napa.get_windowed_fft(n, "float", forward=True, scale="sqrt")
+    x = rand_c(34, n)
+    y = x.copy()
+    assert fun(y, wr) is y and nre(y, O.fft(x.copy(), scale="sqrt", window=wr)) <= tol(n)
+    with pytest.raises(Exception):
+        napa.get_windowed_fft(n, None)
+
+
 def check_window_functions(napa):
     import napa_fft3_b200 as P
     n = 64
@@ -251,6 +276,21 @@ def check_window_functions(napa):
         assert np.array_equal(napa.window_vector(fn, n), O.window_vector(name, n, param=prm)), name
     g = P.gaussian(np.float32(0.5))
     assert np.array_equal(napa.window_vector(g, n), O.window_vector("gauss*", n, param=0.5))
+    # blackman* with another alpha, the general cosine-series and gaussian*bartlett^x (windowing.lisp:12-20, 36-45)
+    f32 = np.float32
+    bs = lambda i, m: P.blackman_star(f32(0.08), i, m)
+    assert np.array_equal(napa.window_vector(bs, n), O.window_vector("blackman*", n, param=0.08))
+    for coeffs in ((0.3635819, 0.4891775, 0.1365995, 0.0106411),                  # Nuttall, double coefficients
+                   (f32(0.21557895), f32(0.41663158), f32(0.277263158), f32(0.083578947))):   # flat top (4 terms), single
+        cs = lambda i, m: P.cosine_series(i, m, *coeffs)
+        want = np.array([O.cosine_series(i, n, *coeffs) for i in range(n)])
+        assert np.array_equal(napa.window_vector(cs, n), want), coeffs
+    for sigma, power in ((0.4, 2), (0.25, 3), (0.5, 1)):
+        gb = P.gaussian_bartlett_x(f32(sigma), power)
+        assert gb is P.gaussian_bartlett_x(f32(sigma), power)                       # same closure for the same parameters
+        want = np.array([O.gaussian_bartlett_x(i, n, f32(sigma), power) for i in range(n)])
+        assert np.array_equal(napa.window_vector(gb, n), want), (sigma, power)
+    assert P.gaussian(f32(0.5)) is g
     assert napa.window_vector(P.hann, n) is napa.window_vector(P.hann, n)          # cached
     assert np.array_equal(napa.window_vector(P.hann, n, bit_reverse=True), O.window_vector("hann", n, bit_reverse=True))
 

@@ -30,7 +30,7 @@ def test_product_library_exports_abi(product_so):
     lib = C.CDLL(product_so)
     for sym in header_symbols():
         assert hasattr(lib, sym), sym
-    assert lib.napafft_abi_version() == 1
+    assert lib.napafft_abi_version() == 2
 
 
 def test_emulation_library_exports_same_abi():

@@ -178,3 +178,26 @@ def test_bit_reverse_batches(napa, n, batch):
     assert np.array_equal(napa.bit_reverse_batch(x.copy()), x[:, p])
     xr = np.ascontiguousarray(x.real)
     assert np.array_equal(napa.bit_reverse_batch(xr.copy()), xr[:, p])
+
+
+@pytest.mark.parametrize("n", [8, 256, 1 << 14])
+def test_get_windowed_fft(napa, n):
+    S.check_get_windowed_fft(napa, n)
+
+
+@pytest.mark.parametrize("lgN", [16, 20])
+def test_distributed_pipeline_single_rank(napa, lgN):
+    """napafft_dist_c2c_dev with one rank (the exchange is a copy): chunked column FFTs with the fused global twiddle,
+    the [chunk][rank][row][Bc] exchange layout, row FFTs reading it in place; library-driven and host-carried exchange"""
+    import torch
+    from napa_fft3_b200.dist import DistributedFFT
+    N = 1 << lgN
+    x = S.rand_c(1005, N)
+    ref = np.fft.fft(x)
+    for native in (True, False):
+        f = DistributedFFT(lgN, napa.b, None, torch.device("cpu"), native=native)
+        xl = torch.from_numpy(f.scatter_time(x))
+        Xl = f.forward(xl)
+        assert S.nre(Xl.numpy(), ref[f.freq_index()]) <= S.tol(N)
+        assert S.nre(f.inverse(Xl).numpy(), f.scatter_time(x)) <= S.tol(N)
+    assert f.nch > 1

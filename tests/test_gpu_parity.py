@@ -168,24 +168,42 @@ def test_launch_counter_moves(napa):
     assert b.launch_count() > before
 
 
-@pytest.mark.parametrize("lgN", [16, 22, 26])
+@pytest.mark.parametrize("lgN", [16, 22, 26, 28])
 def test_distributed_building_blocks_single_rank(napa, lgN):
-    """the device kernels of the distributed four-step (column-axis transform with fused global
-    twiddle, re-layout, batched rows) on one GPU: P = 1 makes the exchange a copy"""
+    """the device pipeline of the distributed four-step (chunked column FFTs with the fused global twiddle, exchange
+    layout, row FFTs reading it in place -- single-pass rows up to 2^26, two-pass rows at 2^28) on one GPU through
+    napafft_dist_c2c_dev: P = 1 makes the exchange a copy on the communication stream"""
     import torch
     import napa_fft3_b200 as P
     from napa_fft3_b200.dist import DistributedFFT
     dev = torch.device("cuda:0")
-    f = DistributedFFT(lgN, P.default_binding(), None, dev)
-    x = S.rand_c(1005, 1 << lgN)
-    ref = np.fft.fft(x)
-    Xl = f.forward(torch.from_numpy(f.scatter_time(x)).to(dev))
-    torch.cuda.synchronize()
-    want = ref[f.freq_index()]
-    assert S.nre(Xl.cpu().numpy(), want) <= S.tol(1 << lgN)
-    back = f.inverse(Xl)
-    torch.cuda.synchronize()
-    assert S.nre(back.cpu().numpy().reshape(-1), x.reshape(f.N1, f.N2).reshape(-1)) <= S.tol(1 << lgN)
+    for native in ((True, False) if lgN == 22 else (True,)):
+        f = DistributedFFT(lgN, P.default_binding(), None, dev, native=native)
+        N = 1 << lgN
+        if lgN <= 26:
+            x = S.rand_c(1005, N)
+            xl = torch.from_numpy(f.scatter_time(x)).to(dev)
+            want, sel = np.fft.fft(x)[f.freq_index()], None
+        else:
+            # too large for a host DFT: impulses, whose spectrum is known in closed form, on sampled bins
+            rng = np.random.Generator(np.random.Philox(lgN))
+            pos = np.unique(np.concatenate([[0, 1, N - 1, N // 2 + 1], rng.integers(0, N, 12)]))
+            amp = rng.uniform(-1, 1, len(pos)) + 1j * rng.uniform(-1, 1, len(pos))
+            xl = torch.zeros((f.N1, f.B), dtype=torch.complex128, device=dev)
+            xl.view(-1)[torch.from_numpy(pos).to(dev)] = torch.from_numpy(amp).to(dev)
+            sel = np.unique(np.concatenate([[0, 1, N - 1, N // 2], rng.integers(0, N, 500)]))      # element index of [R][N2] (P = 1)
+            k = (sel // f.N2) + f.N1 * (sel % f.N2)                                                 # X[k1 + N1 k2] at row k1, column k2
+            ph = (pos[None, :].astype(object) * k[:, None].astype(object)) % N
+            want = (amp[None, :] * np.exp(-2j * np.pi * ph.astype(np.float64) / N)).sum(axis=1)
+        Xl = f.forward(xl)
+        torch.cuda.synchronize()
+        got = Xl.cpu().numpy() if sel is None else Xl.view(-1)[torch.from_numpy(sel).to(dev)].cpu().numpy()
+        assert S.nre(got, want) <= S.tol(N), (lgN, native)
+        back = f.inverse(Xl)
+        torch.cuda.synchronize()
+        assert (torch.linalg.norm(back - xl) / torch.linalg.norm(xl)).item() <= S.tol(N), (lgN, native)
+        del Xl, back, xl
+        torch.cuda.empty_cache()
 
 
 def test_fused_kernel_schedules_gpu():
@@ -255,3 +273,108 @@ def test_bit_reverse_batches(napa, n, batch):
     assert np.array_equal(napa.bit_reverse_batch(x.copy()), x[:, p])
     xr = np.ascontiguousarray(x.real)
     assert np.array_equal(napa.bit_reverse_batch(xr.copy()), xr[:, p])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [8, 256, 1 << 14])
+def test_get_windowed_fft(napa, n):
+    S.check_get_windowed_fft(napa, n)
+
+
+def _sparse_dft_check(napa_binding, lg, in_order, in_place):
+    """Device-resident transform of a handful of impulses: X[k] = sum_j a_j W^{p_j k} is known in closed form, so sampled
+    bins of a transform far too large for the CPU oracle can be checked to the stated tolerance (1e-13 log2 n)."""
+    import torch
+    b = napa_binding
+    n = 1 << lg
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.Generator(np.random.Philox(lg))
+    pos = np.unique(np.concatenate([[0, 1, n - 1, n // 2, n // 2 + 1], rng.integers(0, n, 27)]))
+    amp = rng.uniform(-1, 1, len(pos)) + 1j * rng.uniform(-1, 1, len(pos))
+    x = torch.zeros(n, dtype=torch.complex128, device=dev)
+    x[torch.from_numpy(pos).to(dev)] = torch.from_numpy(amp).to(dev)
+    y = x if in_place else torch.empty_like(x)
+    b.c2c_dev(x.data_ptr(), y.data_ptr(), n, 1, n, 1, 0, int(in_order), None, 0, 0, st)
+    torch.cuda.synchronize()
+    ks = np.unique(np.concatenate([[0, 1, 2, n - 1, n // 2, n // 4 + 3], rng.integers(0, n, 250)]))
+    mem = ks if in_order else S_rev(ks, lg)
+    got = y[torch.from_numpy(mem).to(dev)].cpu().numpy()
+    # exact phases: reduce p*k mod n in integers before going to floating point
+    ph = (pos[None, :].astype(object) * ks[:, None].astype(object)) % n
+    want = (amp[None, :] * np.exp(-2j * np.pi * ph.astype(np.float64) / n)).sum(axis=1)
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err <= S.tol(n), (lg, in_order, err)
+    del x, y
+    torch.cuda.empty_cache()
+
+
+def S_rev(k, lg):
+    k = np.asarray(k, dtype=np.uint64)
+    r = np.zeros_like(k)
+    for i in range(lg):
+        r |= ((k >> np.uint64(i)) & np.uint64(1)) << np.uint64(lg - 1 - i)
+    return r.astype(np.int64)
+
+
+@pytest.mark.parametrize("lg,in_order", [(26, True), (28, True), (28, False), (30, True)])
+def test_very_large_single_transform(napa, lg, in_order):
+    """2^26 .. 2^30 on one GPU (three-digit plans, natural order through the scratch copy), sampled bins"""
+    import napa_fft3_b200 as P
+    _sparse_dft_check(P.default_binding(), lg, in_order, in_place=False)
+
+
+def test_two_to_the_31_in_place_fallback(napa):
+    """2^31 points (32 GiB) in place and in order: too large for the scratch copy (interface.lisp:86 allows sizes up
+    to 2^32), so the natural order comes from the in-place bit-reversed pipeline plus the bit-reversal pass"""
+    import torch
+    import napa_fft3_b200 as P
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs 40 GiB of free device memory")
+    _sparse_dft_check(P.default_binding(), 31, True, in_place=True)
+
+
+def test_concurrent_host_threads(napa):
+    """distinct vectors from several host threads at once (the reference allows it, README:811-814): every thread owns its
+    staging streams and buffers, only the launch step is serialised"""
+    import threading
+    from oracle import napa_oracle as O
+    n, batch, nthreads = 1 << 12, 300, 4
+    xs = [np.stack([S.rand_c(1000 * t + i, n) for i in range(8)] * ((batch + 7) // 8))[:batch].copy() for t in range(nthreads)]
+    outs, errs = [None] * nthreads, []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                got = napa.fft_batch(xs[t].copy(), in_order=(t % 2 == 0), scale="sqrt")
+                outs[t] = napa.fft_batch(got, direction=-1, in_order=(t % 2 == 0), scale="sqrt")
+                r = napa.rfft(np.ascontiguousarray(xs[t][0].real))
+                assert S.nre(r, O.rfft(np.ascontiguousarray(xs[t][0].real))) <= S.tol(n)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for t in range(nthreads):
+        assert S.nre(outs[t], xs[t]) <= S.tol(n), t
+
+
+def test_distributed_fft_multi_gpu():
+    """the distributed four-step over every GPU of the box (skipped on a single GPU): tools/dist_check.py under
+    torchrun checks sampled rows of the result against the CPU oracle and the round trip"""
+    import subprocess
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 1 << (ngpu.bit_length() - 1)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py"), "24"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0 and "dist ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
