@@ -91,7 +91,8 @@ struct State {
     int fused_prefetch = 1;               // L2 prefetch of each CTA's next pass-A tile
     int fused_tma = 0;                    // NAPAFFT_FUSED_TMA=1: TMA-fed warp-specialised variant of the fused kernel (2^14 .. 2^16)
     int fused_lead = 0;                   // units pass A runs ahead of pass B (0 = default 2)
-    int dist_chunks = 4;                  // distributed four-step: column chunks whose exchange overlaps the next chunk's column FFTs
+    int dist_chunks = 8;                  // distributed four-step: column chunks whose exchange overlaps the next chunk's column FFTs
+    int dist_peer_copy = 1;               // exchange by copy-engine transfers into IPC-mapped peer buffers (0: ncclSend / ncclRecv)
     bool use_fused = false;               // fused single-launch plans for 2^14 .. 2^20 (NAPAFFT_FUSED=1); measured: no faster than one launch per digit pass
     bool attrs_set = false;
     int num_sms = 148;
@@ -1213,7 +1214,7 @@ NAPA_API int napafft_init(int device) {
     // tunables: defaults first (a re-init after napafft_shutdown must not inherit the previous settings)
     { State d; G.chunk_bytes = d.chunk_bytes; G.zero_copy_bytes = d.zero_copy_bytes; G.max_scratch_bytes = d.max_scratch_bytes;
       G.fused_unit_bytes = d.fused_unit_bytes; G.fused_upg = d.fused_upg; G.fused_grid = d.fused_grid; G.use_fused = d.use_fused;
-      G.fused_prefetch = d.fused_prefetch; G.fused_tma = d.fused_tma; G.fused_lead = d.fused_lead; G.dist_chunks = d.dist_chunks; }
+      G.fused_prefetch = d.fused_prefetch; G.fused_tma = d.fused_tma; G.fused_lead = d.fused_lead; G.dist_chunks = d.dist_chunks; G.dist_peer_copy = d.dist_peer_copy; }
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_ZERO_COPY_KB")) G.zero_copy_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_MAX_SCRATCH_KB")) G.max_scratch_bytes = (size_t)atoll(env) << 10;
@@ -1225,6 +1226,7 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_FUSED_TMA")) G.fused_tma = atoi(env);
     if (const char *env = getenv("NAPAFFT_FUSED_LEAD")) G.fused_lead = atoi(env);
     if (const char *env = getenv("NAPAFFT_DIST_CHUNKS")) G.dist_chunks = atoi(env);
+    if (const char *env = getenv("NAPAFFT_DIST_PEER_COPY")) G.dist_peer_copy = atoi(env);
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;
@@ -1468,7 +1470,7 @@ static int dist_geom(int lgN, int P, int nch, DistGeom *g) {
     g->B = g->N2 / P; g->R = g->N1 / P;
     // a chunk holds whole tiles of every pass that touches it (a tile spans at most 128 adjacent columns / points)
     const size_t min_bc = 128;
-    if (nch <= 0) nch = 4;
+    if (nch <= 0) nch = 8;
     while (nch > 1 && (g->B % nch || g->B / nch < min_bc)) nch >>= 1;
     if (g->B < min_bc) return fail(NAPA_E_UNSUPPORTED, "fewer than %zu columns per rank (2^%d points over %d ranks)", min_bc, lgN, P);
     if (!pow2((size_t)nch)) return fail(NAPA_E_UNSUPPORTED, "the number of chunks must be a power of two");
@@ -1508,6 +1510,8 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi NC;
@@ -1519,7 +1523,7 @@ static int nccl_load() {
 #define NAPA_NCCL_SYM(field, sym) do { *(void **)(&NC.field) = dlsym(NC.lib, sym); if (!NC.field) { NC.lib = nullptr; return fail(NAPA_E_NCCL, "%s missing from the NCCL library", sym); } } while (0)
     NAPA_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NAPA_NCCL_SYM(CommInitRank, "ncclCommInitRank"); NAPA_NCCL_SYM(CommDestroy, "ncclCommDestroy");
     NAPA_NCCL_SYM(GroupStart, "ncclGroupStart"); NAPA_NCCL_SYM(GroupEnd, "ncclGroupEnd"); NAPA_NCCL_SYM(Send, "ncclSend"); NAPA_NCCL_SYM(Recv, "ncclRecv");
-    NAPA_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+    NAPA_NCCL_SYM(GetErrorString, "ncclGetErrorString"); NAPA_NCCL_SYM(AllGather, "ncclAllGather"); NAPA_NCCL_SYM(AllReduce, "ncclAllReduce");
 #undef NAPA_NCCL_SYM
     return NAPA_OK;
 }
@@ -1538,23 +1542,84 @@ struct DistState {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready[16] = {}, ev_done[16] = {};
     cplx *send = nullptr, *recv = nullptr; size_t buf_elems = 0;
+    // peer-copy exchange: every rank's recv buffer mapped into this process (CUDA IPC); the all-to-all is then P - 1
+    // copy-engine transfers over NVLink that use no SM, so it overlaps the column FFTs without competing with them
+    cplx *peer_recv[64] = {};
+    bool peer_ok = false;
+    int *sync_word = nullptr;                    // operand of the tiny all-reduces that fence the copies across ranks
 };
 static DistState D;
+
+// Map every peer's receive buffer (collective: all ranks allocate the same size in the same call).  Any failure on any
+// rank leaves peer_ok false everywhere and the exchange falls back to ncclSend / ncclRecv.
+static int dist_map_peers() {
+    D.peer_ok = false;
+#ifndef NAPA_EMULATE
+    if (D.nranks <= 1 || D.nranks > 64 || !G.dist_peer_copy) return NAPA_OK;
+    if (!D.sync_word) CU(cudaMalloc((void **)&D.sync_word, 256));
+    cudaIpcMemHandle_t mine;
+    int ok = cudaIpcGetMemHandle(&mine, D.recv) == cudaSuccess;
+    cudaGetLastError();
+    unsigned char *hbuf = nullptr;
+    CU(cudaMalloc((void **)&hbuf, (size_t)D.nranks * sizeof mine));
+    CU(cudaMemcpy(hbuf + (size_t)D.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NCCL(NC.AllGather(hbuf + (size_t)D.rank * sizeof mine, hbuf, sizeof mine, ncclChar, D.comm, D.comm_stream));
+    CU(cudaStreamSynchronize(D.comm_stream));
+    std::vector<cudaIpcMemHandle_t> all(D.nranks);
+    CU(cudaMemcpy(all.data(), hbuf, (size_t)D.nranks * sizeof mine, cudaMemcpyDeviceToHost));
+    CU(cudaFree(hbuf));
+    for (int r = 0; r < D.nranks && ok; r++) {
+        if (r == D.rank) { D.peer_recv[r] = D.recv; continue; }
+        void *pp = nullptr;
+        if (cudaIpcOpenMemHandle(&pp, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        D.peer_recv[r] = (cplx *)pp;
+    }
+    // everyone or no one
+    CU(cudaMemcpy(D.sync_word, &ok, sizeof ok, cudaMemcpyHostToDevice));
+    NCCL(NC.AllReduce(D.sync_word, D.sync_word, 1, ncclInt, ncclMin, D.comm, D.comm_stream));
+    CU(cudaStreamSynchronize(D.comm_stream));
+    CU(cudaMemcpy(&ok, D.sync_word, sizeof ok, cudaMemcpyDeviceToHost));
+    D.peer_ok = ok != 0;
+#endif
+    return NAPA_OK;
+}
+static void dist_unmap_peers() {
+#ifndef NAPA_EMULATE
+    for (int r = 0; r < 64; r++) {
+        if (D.peer_recv[r] && r != D.rank) cudaIpcCloseMemHandle(D.peer_recv[r]);
+        D.peer_recv[r] = nullptr;
+    }
+    cudaGetLastError();
+#endif
+    D.peer_ok = false;
+}
+// cross-rank fence on the communication stream: returns (in stream order) once every rank has reached it
+static int dist_fence() {
+#ifndef NAPA_EMULATE
+    if (D.nranks > 1) NCCL(NC.AllReduce(D.sync_word, D.sync_word, 1, ncclInt, ncclSum, D.comm, D.comm_stream));
+#endif
+    return NAPA_OK;
+}
 
 static int dist_buffers(size_t elems) {
     if (D.buf_elems >= elems) return NAPA_OK;
     CU(cudaDeviceSynchronize());
+    dist_unmap_peers();
     if (D.send) CU(cudaFree(D.send));
     if (D.recv) CU(cudaFree(D.recv));
     D.send = D.recv = nullptr; D.buf_elems = 0;
     CU(cudaMalloc((void **)&D.send, elems * sizeof(cplx)));
     CU(cudaMalloc((void **)&D.recv, elems * sizeof(cplx)));
     D.buf_elems = elems;
+    OK(dist_map_peers());
     return NAPA_OK;
 }
 static int dist_events() {
     if (D.comm_stream) return NAPA_OK;
-    CU(cudaStreamCreateWithFlags(&D.comm_stream, cudaStreamNonBlocking));
+    // highest priority: the exchange kernels need only a few SMs but must get them while column passes fill the machine
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&D.comm_stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 16; i++) {
         CU(cudaEventCreateWithFlags(&D.ev_ready[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&D.ev_done[i], cudaEventDisableTiming));
@@ -1571,6 +1636,15 @@ static int dist_exchange_chunk(const DistGeom &g, int c, const cplx *from, cplx 
 #ifdef NAPA_EMULATE
     return fail(NAPA_E_NCCL, "no NCCL in the emulation build");
 #else
+    if (D.peer_ok && to == D.recv) {
+        // slab h of my chunk goes straight into rank h's receive buffer, at my rank's place; copy engines, no SM
+        for (int i = 0; i < g.P; i++) {
+            const int h = (D.rank + i) % g.P;
+            CU(cudaMemcpyAsync(D.peer_recv[h] + off + (size_t)D.rank * slab, from + off + (size_t)h * slab, slab * sizeof(cplx),
+                               cudaMemcpyDeviceToDevice, D.comm_stream));
+        }
+        return NAPA_OK;
+    }
     NCCL(NC.GroupStart());
     for (int h = 0; h < g.P; h++) {
         NCCL(NC.Send(from + off + (size_t)h * slab, 2 * slab, ncclDouble, h, D.comm, D.comm_stream));
@@ -1587,13 +1661,19 @@ static int exec_dist(cplx *src_local, cplx *dst_local, int lgN, int dir, int nch
     if (g.nch > 16) return fail(NAPA_E_UNSUPPORTED, "at most 16 chunks");
     OK(dist_events());
     OK(dist_buffers(g.N1 * g.B));
+    // Peer copies write into OTHER ranks' receive buffers: fence A (every rank is done reading its buffer: the
+    // communication stream is already behind the previous call's compute) before the first copy, fence B (every rank's
+    // copies have landed) before the data is used.  ncclSend / ncclRecv pairs synchronise by themselves.
+    const bool fenced = D.peer_ok && g.P > 1;
     if (dir > 0) {
+        if (fenced) OK(dist_fence());
         for (int c = 0; c < g.nch; c++) {
             OK(dist_cols(g, D.rank, c, +1, src_local, D.send, st));
             CU(cudaEventRecord(D.ev_ready[c], st));
             CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[c], 0));
             OK(dist_exchange_chunk(g, c, D.send, D.recv));
         }
+        if (fenced) OK(dist_fence());
         CU(cudaEventRecord(D.ev_done[0], D.comm_stream));
         CU(cudaStreamWaitEvent(st, D.ev_done[0], 0));
         OK(dist_rows(g, +1, D.recv, dst_local, st));
@@ -1601,8 +1681,10 @@ static int exec_dist(cplx *src_local, cplx *dst_local, int lgN, int dir, int nch
         OK(dist_rows(g, -1, D.send, src_local, st));
         CU(cudaEventRecord(D.ev_ready[0], st));
         CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[0], 0));
+        if (fenced) OK(dist_fence());
         for (int c = 0; c < g.nch; c++) {
             OK(dist_exchange_chunk(g, c, D.send, D.recv));
+            if (fenced) OK(dist_fence());
             CU(cudaEventRecord(D.ev_done[c], D.comm_stream));
             CU(cudaStreamWaitEvent(st, D.ev_done[c], 0));
             OK(dist_cols(g, D.rank, c, -1, dst_local, D.recv, st));
@@ -1647,6 +1729,8 @@ NAPA_API int napafft_dist_init(const void *unique_id128, int rank, int nranks) {
     return NAPA_OK;
 }
 static void dist_release() {
+    dist_unmap_peers();
+    if (D.sync_word) cudaFree(D.sync_word);
 #ifndef NAPA_EMULATE
     if (D.comm) { NC.CommDestroy(D.comm); D.comm = nullptr; }
 #endif

@@ -126,3 +126,25 @@
                                               (sb-sys:vector-sap filter-rev) (sb-sys:vector-sap window)
                                               chunk-size (sb-sys:vector-sap destination))))
     destination))
+
+
+;;; new export: ONE transform of 2^LGN points spread over the NRANKS processes that called DIST-INIT (BASELINE config 5).
+;;; LOCAL-IN is this rank's block in the time layout ([N1][B] row-major, columns [rank*B, (rank+1)*B) of the [N1][N2] view
+;;; of the vector) for :fwd, or in the frequency layout ([R][N2], rows k1 of X[k1 + N1*k2]) for :inv; the result is the other
+;;; layout (include/napafft.h).  :inv scales by 1/N, like IFFT's default.
+(defun dist-init (unique-id rank nranks)
+  (declare (type (simple-array (unsigned-byte 8) (128)) unique-id))
+  (with-pinned-objects (unique-id)
+    (check (napafft-dist-init (vector-sap unique-id) rank nranks))))
+
+(defun dist-unique-id ()
+  (let ((id (make-array 128 :element-type '(unsigned-byte 8))))
+    (with-pinned-objects (id)
+      (check (napafft-dist-unique-id (vector-sap id))))
+    id))
+
+(defun dist-fft (local-in local-out lgn &key (direction 1))
+  (declare (type complex-sample-array local-in local-out))
+  (with-pinned-objects (local-in local-out)
+    (check (napafft-dist-c2c (vector-sap local-in) (vector-sap local-out) lgn (direction-code direction))))
+  local-out)

@@ -47,6 +47,17 @@
   (dir int) (scale int) (in-order int) (window system-area-pointer) (window-type int)
   (window-per-batch int))
 
+;; One transform over several GPUs (one SBCL process per GPU): include/napafft.h, "napafft_dist_*".  Rank 0 obtains the
+;; 128-byte id and hands it to the other processes by whatever channel the application has (a file, a socket).
+(define-alien-routine "napafft_dist_unique_id" int (out128 system-area-pointer))
+(define-alien-routine "napafft_dist_init" int (unique-id128 system-area-pointer) (rank int) (nranks int))
+(define-alien-routine "napafft_dist_shutdown" int)
+(define-alien-routine "napafft_dist_c2c" int
+  (src-local system-area-pointer) (dst-local system-area-pointer) (lgn int) (dir int))
+(define-alien-routine "napafft_dist_geometry" int
+  (lgn int) (nranks int) (n1 (* size-t)) (n2 (* size-t)) (cols-per-rank (* size-t)) (rows-per-rank (* size-t))
+  (nchunks (* int)))
+
 (defun check (status)
   (unless (zerop status)
     (error 'napafft-error :status status :message (napafft-last-error)))

@@ -20,7 +20,8 @@
            "RFFT" "RIFFT"
            "WINDOWED-RFFT" "WINDOWED-RIFFT"
            ;; new exports of the B200 build (batched / device-resident paths)
-           "FFT-BATCH" "FILTER-CHUNKS" "NAPAFFT-ERROR"))
+           "FFT-BATCH" "FILTER-CHUNKS" "NAPAFFT-ERROR"
+           "DIST-INIT" "DIST-UNIQUE-ID" "DIST-FFT"))
 
 (defpackage "NAPA-FFT.B200"
   (:use "CL" "SB-ALIEN" "SB-SYS" "NAPA-FFT"))
