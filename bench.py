@@ -520,7 +520,10 @@ def measure_c5(args, torch, dist, napa, b, world, rank, local, dev, lg, steps, w
     a2a_bytes = f.alltoall_bytes_per_rank()
     rec = {
         "workload": "c5", "description": WORKLOADS["c5"][2], "log2n": lg, "n": n, "N1": f.N1, "N2": f.N2, "n_gpus": world,
-        "exchange": "library-owned NCCL communicator (napafft_dist_c2c_dev), %d column chunks" % f.nch if f.native else "torch.distributed per chunk",
+        "exchange": ("%s, %d column chunks overlapping the column FFTs (napafft_dist_c2c_dev)" % (
+            {0: "?", 1: "single rank: device copy", 2: "ncclSend / ncclRecv on the library's communicator",
+             3: "copy-engine transfers into IPC-mapped peer buffers, fenced by NCCL all-reduces"}[int(b.L.napafft_dist_exchange_mode())], f.nch))
+        if f.native else "torch.distributed all_to_all_single per chunk",
         "ms_per_step": ms_per_step, "steps": steps, "value": 5.0 * n * lg / (ms_per_step * 1e-3) / 1e9, "unit": "GFLOP/s",
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

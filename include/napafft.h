@@ -161,6 +161,10 @@ int napafft_dist_init(const void *unique_id128, int rank, int nranks);
 int napafft_dist_shutdown(void);
 int napafft_dist_c2c_dev(const void *src_local, void *dst_local, int lgN, int dir, void *stream);
 int napafft_dist_c2c(const double *src_local, double *dst_local, int lgN, int dir);
+/* how the exchange travels: 0 not initialised, 1 one rank (device copy), 2 ncclSend / ncclRecv, 3 copy-engine
+ * transfers over NVLink into the peers' receive buffers, mapped through CUDA IPC and fenced by tiny all-reduces
+ * (the default when IPC mapping succeeds on every rank; NAPAFFT_DIST_PEER_COPY=0 forces 2).  Not a status code. */
+int napafft_dist_exchange_mode(void);
 /* geometry of the layouts above for 2^lgN points over nranks ranks (any output pointer may be NULL) */
 int napafft_dist_geometry(int lgN, int nranks, size_t *n1, size_t *n2, size_t *cols_per_rank, size_t *rows_per_rank,
                           int *nchunks);

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "napafft_cmul_dev", "napafft_c2c_cols_dev", "napafft_relayout_dev", "napafft_dev_alloc", "napafft_dev_free", "napafft_dev_upload", "napafft_dev_download",
     "napafft_dev_sync", "napafft_scale_factor", "napafft_radix2_twiddle",
     "napafft_dist_unique_id", "napafft_dist_init", "napafft_dist_shutdown", "napafft_dist_c2c_dev", "napafft_dist_c2c",
-    "napafft_dist_geometry", "napafft_dist_cols_dev", "napafft_dist_rows_dev",
+    "napafft_dist_geometry", "napafft_dist_cols_dev", "napafft_dist_rows_dev", "napafft_dist_exchange_mode",
 ]
 
 

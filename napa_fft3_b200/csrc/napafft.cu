@@ -91,7 +91,7 @@ struct State {
     int fused_prefetch = 1;               // L2 prefetch of each CTA's next pass-A tile
     int fused_tma = 0;                    // NAPAFFT_FUSED_TMA=1: TMA-fed warp-specialised variant of the fused kernel (2^14 .. 2^16)
     int fused_lead = 0;                   // units pass A runs ahead of pass B (0 = default 2)
-    int dist_chunks = 8;                  // distributed four-step: column chunks whose exchange overlaps the next chunk's column FFTs
+    int dist_chunks = 0;                  // distributed four-step: column chunks whose exchange overlaps the next chunk's column FFTs
     int dist_peer_copy = 1;               // exchange by copy-engine transfers into IPC-mapped peer buffers (0: ncclSend / ncclRecv)
     bool use_fused = false;               // fused single-launch plans for 2^14 .. 2^20 (NAPAFFT_FUSED=1); measured: no faster than one launch per digit pass
     bool attrs_set = false;
@@ -1470,7 +1470,7 @@ static int dist_geom(int lgN, int P, int nch, DistGeom *g) {
     g->B = g->N2 / P; g->R = g->N1 / P;
     // a chunk holds whole tiles of every pass that touches it (a tile spans at most 128 adjacent columns / points)
     const size_t min_bc = 128;
-    if (nch <= 0) nch = 8;
+    if (nch <= 0) nch = P <= 2 ? 8 : 4;
     while (nch > 1 && (g->B % nch || g->B / nch < min_bc)) nch >>= 1;
     if (g->B < min_bc) return fail(NAPA_E_UNSUPPORTED, "fewer than %zu columns per rank (2^%d points over %d ranks)", min_bc, lgN, P);
     if (!pow2((size_t)nch)) return fail(NAPA_E_UNSUPPORTED, "the number of chunks must be a power of two");
@@ -1784,6 +1784,14 @@ NAPA_API int napafft_dist_c2c(const double *src_local, double *dst_local, int lg
     }
     cudaFree(d_in); cudaFree(d_out);
     return rc;
+}
+// how the exchange is carried: 0 = not initialised, 1 = single rank (device copy), 2 = ncclSend / ncclRecv,
+// 3 = copy-engine transfers into IPC-mapped peer buffers (decided when the buffers are first allocated)
+NAPA_API int napafft_dist_exchange_mode(void) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!D.nranks) return 0;
+    if (D.nranks == 1) return 1;
+    return D.peer_ok || (!D.buf_elems && G.dist_peer_copy) ? 3 : 2;
 }
 NAPA_API int napafft_dist_geometry(int lgN, int nranks, size_t *n1, size_t *n2, size_t *cols_per_rank, size_t *rows_per_rank, int *nchunks) {
     OK(napafft_enter());
