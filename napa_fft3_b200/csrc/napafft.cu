@@ -236,25 +236,32 @@ static int ensure_scratch(cudaStream_t st, size_t bytes, cplx **out) {
 // tile kinds (lane maps): 0 column-like, 1 row-like, 2 row-like load + transposed store
 enum { KIND_COL = 0, KIND_ROW = 1, KIND_ROWT = 2 };
 typedef void (*pass_fn)(const PassParams);
-template <int K, bool LEAN> static pass_fn pass_kernel_k(int l) {
+template <int K, int V> static pass_fn pass_kernel_k(int l) {
     switch (l) {
-    case 4: return napa::fft_pass_kernel<4, K, LEAN>;
-    case 5: return napa::fft_pass_kernel<5, K, LEAN>;
-    case 6: return napa::fft_pass_kernel<6, K, LEAN>;
-    case 7: return napa::fft_pass_kernel<7, K, LEAN>;
-    case 8: return napa::fft_pass_kernel<8, K, LEAN>;
-    case 9: return napa::fft_pass_kernel<9, K, LEAN>;
-    case 10: return napa::fft_pass_kernel<10, K, LEAN>;
-    case 11: return napa::fft_pass_kernel<11, K, LEAN>;
-    case 12: return napa::fft_pass_kernel<12, K, LEAN>;
-    case 13: return napa::fft_pass_kernel<13, K, LEAN>;
+    case 4: return napa::fft_pass_kernel<4, K, V>;
+    case 5: return napa::fft_pass_kernel<5, K, V>;
+    case 6: return napa::fft_pass_kernel<6, K, V>;
+    case 7: return napa::fft_pass_kernel<7, K, V>;
+    case 8: return napa::fft_pass_kernel<8, K, V>;
+    case 9: return napa::fft_pass_kernel<9, K, V>;
+    case 10: return napa::fft_pass_kernel<10, K, V>;
+    case 11: return napa::fft_pass_kernel<11, K, V>;
+    case 12: return napa::fft_pass_kernel<12, K, V>;
+    case 13: return napa::fft_pass_kernel<13, K, V>;
     }
     return nullptr;
 }
-static pass_fn pass_kernel(int l, int kind, bool lean) {
+// variant: 0 every fusion path, 1 lean, 2 lean + window (napafft_kernels.cuh: variant_flags)
+static int pass_variant(unsigned flags) {
+    if ((flags & ~napa::LEAN_FLAGS) == 0) return 1;
+    if ((flags & ~napa::WINLEAN_FLAGS) == 0) return 2;
+    return 0;
+}
+static pass_fn pass_kernel(int l, int kind, int variant) {
     if (l < 7 && kind != KIND_ROW) kind = KIND_COL;   // small L: one lane map (see kind_lm); KIND_ROW = dense-rows variant
-    if (lean) return kind == KIND_COL ? pass_kernel_k<0, true>(l) : (kind == KIND_ROW ? pass_kernel_k<1, true>(l) : pass_kernel_k<2, true>(l));
-    return kind == KIND_COL ? pass_kernel_k<0, false>(l) : (kind == KIND_ROW ? pass_kernel_k<1, false>(l) : pass_kernel_k<2, false>(l));
+    if (variant == 1) return kind == KIND_COL ? pass_kernel_k<0, 1>(l) : (kind == KIND_ROW ? pass_kernel_k<1, 1>(l) : pass_kernel_k<2, 1>(l));
+    if (variant == 2) return kind == KIND_COL ? pass_kernel_k<0, 2>(l) : (kind == KIND_ROW ? pass_kernel_k<1, 2>(l) : pass_kernel_k<2, 2>(l));
+    return kind == KIND_COL ? pass_kernel_k<0, 0>(l) : (kind == KIND_ROW ? pass_kernel_k<1, 0>(l) : pass_kernel_k<2, 0>(l));
 }
 
 static int set_kernel_attrs() {
@@ -263,8 +270,8 @@ static int set_kernel_attrs() {
         for (int kind = 0; kind < 3; kind++) {
             size_t sm = napa::kind_smem_bytes(l, kind);
             if (sm > 48 * 1024) {
-                CU(cudaFuncSetAttribute((const void *)pass_kernel(l, kind, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                CU(cudaFuncSetAttribute((const void *)pass_kernel(l, kind, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                for (int v = 0; v < 3; v++)
+                    CU(cudaFuncSetAttribute((const void *)pass_kernel(l, kind, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             }
         }
     G.attrs_set = true;
@@ -283,7 +290,7 @@ static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStr
                            p.dst_batch_stride == (1LL << l) && !(p.flags & napa::PF_RIFFT_PRE);
         kind = dense ? KIND_ROW : KIND_COL;
     }
-    pass_fn fn = pass_kernel(l, kind, (p.flags & ~napa::LEAN_FLAGS) == 0);
+    pass_fn fn = pass_kernel(l, kind, pass_variant(p.flags));
     NAPA_LAUNCH(fn, (unsigned)ntiles, napa::plan_threads(l), napa::kind_smem_bytes(l, kind), st, p);
     g_launches++;
     return NAPA_OK;

@@ -637,12 +637,22 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         // real window values are fetched first: they do not depend on the data and their L2
         // latency then overlaps the data wait
         double wv[16];
+        // window index = memory position; when the registers hold memory positions t + m*T (no permutation between
+        // memory and registers on this side) it advances like the data pointer: one base + m * step
+        const bool win_linear = !(flags & PF_WIN_REV) && (!(flags & PF_IN_REV) || in_reorder);
         if (flags & PF_WIN_REAL) {
             const double *w = reinterpret_cast<const double *>(p.window) + c.item * p.window_batch_stride;
+            if (win_linear) {
+                const double *w0 = w + s_xoff + (long long)t * s_i;
+                const long long ws = (long long)T * s_i;
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const long long off = s_xoff + (long long)lpos(m) * s_i;
-                wv[m] = __ldg(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
+                for (int m = 0; m < 16; m++) wv[m] = __ldg(w0 + m * ws);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const long long off = s_xoff + (long long)lpos(m) * s_i;
+                    wv[m] = __ldg(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
+                }
             }
         }
         if constexpr (DENSE) {
@@ -713,13 +723,20 @@ __device__ __forceinline__ void run_tile(const PassParams &p, const long long ti
         }
         if (flags & PF_WIN_CPLX) {
             const cplx *w = reinterpret_cast<const cplx *>(p.window) + c.item * p.window_batch_stride;
+            const cplx *w0 = w + s_xoff + (long long)t * s_i;
+            const long long ws = (long long)T * s_i;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 cplx wc[8];
+                if (win_linear) {
 #pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const long long off = s_xoff + (long long)lpos(8 * h + m) * s_i;
-                    wc[m] = ldg_c(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
+                    for (int m = 0; m < 8; m++) wc[m] = ldg_c(w0 + (8 * h + m) * ws);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        const long long off = s_xoff + (long long)lpos(8 * h + m) * s_i;
+                        wc[m] = ldg_c(w + ((flags & PF_WIN_REV) ? rev_bits64(off, p.lgN) : off));
+                    }
                 }
 #pragma unroll
                 for (int m = 0; m < 8; m++) v[8 * h + m] = cmul(v[8 * h + m], wc[m]);
@@ -880,17 +897,21 @@ __host__ __device__ constexpr size_t kind_smem_bytes(int l, int kind) {
 }
 
 // One tile per CTA (single-pass transforms and every pass of multi-pass ones by default).
-// LEAN: compiled without the window / rifft fusion paths (most launches: every non-first pass and
-// un-windowed first passes) -- smaller code, fewer flag tests.
+// VARIANT: which fusion paths are compiled in -- 0 everything (real wrappers: zip, rifft pre-twiddle, rfft / split
+// epilogues), 1 LEAN: none of the optional fusions (every non-first pass and un-windowed first passes), 2 lean + the
+// window multiply.  Smaller code (the full variant of a 2^12 tile is ~100 KB of SASS, far beyond the instruction
+// cache) and fewer flag tests on the launches that dominate the benchmarks.
 constexpr unsigned LEAN_FLAGS = PF_Q_IS_BATCH | PF_IN_REV | PF_OUT_REV | PF_CONJ_IN | PF_CONJ_OUT | PF_TW_LOAD | PF_TW_STORE | PF_SCALE;
-template <int LOG2L, int KIND, bool LEAN>
+constexpr unsigned WINLEAN_FLAGS = LEAN_FLAGS | PF_WIN_REAL | PF_WIN_CPLX | PF_WIN_REV;
+__host__ __device__ constexpr unsigned variant_flags(int v) { return v == 1 ? LEAN_FLAGS : (v == 2 ? WINLEAN_FLAGS : 0xffffffffu); }
+template <int LOG2L, int KIND, int VARIANT>
 __global__ void __launch_bounds__(plan_threads(LOG2L), plan_min_ctas(LOG2L))
 fft_pass_kernel(const PassParams p) {
     NAPA_DYN_SMEM(cplx, sm);
     L2Policies pol{};                                 // plain loads/stores: no L2 policy operands
     NoHook nh;
     // L < 128: KIND 1 selects the dense-rows variant (single-pass batches of back-to-back transforms)
-    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND), SyncAll, false, NoHook, LEAN ? LEAN_FLAGS : 0xffffffffu, false,
+    run_tile<LOG2L, false, kind_lm(LOG2L, KIND), kind_sm(LOG2L, KIND), SyncAll, false, NoHook, variant_flags(VARIANT), false,
              false, (LOG2L < 7 && KIND == 1)>(p, (long long)blockIdx.x, sm, 0, 0, pol, nh);
 }
 
