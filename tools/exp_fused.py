@@ -12,7 +12,9 @@ total = int(sys.argv[1]) << 20
 sizes = [int(a) for a in sys.argv[2].split(",")]
 variants = [v.strip() for v in sys.argv[3].split(";")]
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-b = napa.default_binding()
+b = napa.Binding(os.environ["NAPA_SO"]) if "NAPA_SO" in os.environ else napa.default_binding()
+if "NAPA_SO" in os.environ:
+    b.init(0)
 dev = torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
 x = torch.view_as_complex(torch.rand((total // 16, 2), dtype=torch.float64, device=dev) * 2 - 1).contiguous()
