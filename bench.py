@@ -268,7 +268,7 @@ def main():
     traffic, traffic_src = None, None
     try:
         # DRAM bytes of one whole step summed over its launches, from this round's `ncu --set full` capture of the same
-        # command (tools/profile_c2.sh writes the file next to the summaries it comes from), per launch like `achieved`
+        # command (tools/profile_workload.sh writes the file next to the summaries it comes from), per launch like `achieved`
         t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(wl)
         traffic = float(t["dram_bytes_per_step"]) / max(launches_per_step, 1)
         traffic_src = t.get("source")

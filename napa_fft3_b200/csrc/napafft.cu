@@ -93,6 +93,8 @@ struct State {
     int fused_lead = 0;                   // units pass A runs ahead of pass B (0 = default 2)
     int dist_chunks = 0;                  // distributed four-step: column chunks whose exchange overlaps the next chunk's column FFTs
     int dist_peer_copy = 1;               // exchange by copy-engine transfers into IPC-mapped peer buffers (0: ncclSend / ncclRecv)
+    int dist_row_blocks = 0;              // row blocks of the chunks next to the row stage (0 = 4)
+    int dist_tail_chunks = 0;             // how many chunks are exchanged row block by row block (0 = 1)
     bool use_fused = false;               // fused single-launch plans for 2^14 .. 2^20 (NAPAFFT_FUSED=1); measured: no faster than one launch per digit pass
     bool attrs_set = false;
     int num_sms = 148;
@@ -1221,7 +1223,7 @@ NAPA_API int napafft_init(int device) {
     // tunables: defaults first (a re-init after napafft_shutdown must not inherit the previous settings)
     { State d; G.chunk_bytes = d.chunk_bytes; G.zero_copy_bytes = d.zero_copy_bytes; G.max_scratch_bytes = d.max_scratch_bytes;
       G.fused_unit_bytes = d.fused_unit_bytes; G.fused_upg = d.fused_upg; G.fused_grid = d.fused_grid; G.use_fused = d.use_fused;
-      G.fused_prefetch = d.fused_prefetch; G.fused_tma = d.fused_tma; G.fused_lead = d.fused_lead; G.dist_chunks = d.dist_chunks; G.dist_peer_copy = d.dist_peer_copy; }
+      G.fused_prefetch = d.fused_prefetch; G.fused_tma = d.fused_tma; G.fused_lead = d.fused_lead; G.dist_chunks = d.dist_chunks; G.dist_peer_copy = d.dist_peer_copy; G.dist_row_blocks = d.dist_row_blocks; G.dist_tail_chunks = d.dist_tail_chunks; }
     if (const char *env = getenv("NAPAFFT_CHUNK_MB")) G.chunk_bytes = (size_t)atoll(env) << 20;
     if (const char *env = getenv("NAPAFFT_ZERO_COPY_KB")) G.zero_copy_bytes = (size_t)atoll(env) << 10;
     if (const char *env = getenv("NAPAFFT_MAX_SCRATCH_KB")) G.max_scratch_bytes = (size_t)atoll(env) << 10;
@@ -1234,6 +1236,8 @@ NAPA_API int napafft_init(int device) {
     if (const char *env = getenv("NAPAFFT_FUSED_LEAD")) G.fused_lead = atoi(env);
     if (const char *env = getenv("NAPAFFT_DIST_CHUNKS")) G.dist_chunks = atoi(env);
     if (const char *env = getenv("NAPAFFT_DIST_PEER_COPY")) G.dist_peer_copy = atoi(env);
+    if (const char *env = getenv("NAPAFFT_DIST_ROW_BLOCKS")) G.dist_row_blocks = atoi(env);
+    if (const char *env = getenv("NAPAFFT_DIST_TAIL_CHUNKS")) G.dist_tail_chunks = atoi(env);
     G.num_sms = prop.multiProcessorCount;
     G.device = device;
     G.inited = true;
@@ -1493,14 +1497,17 @@ static int dist_cols(const DistGeom &g, int rank, int c, int dir, cplx *x_local,
     return exec_cols(chunk, g.Bc, x_local + (size_t)c * g.Bc, g.B, g.N1, g.Bc, -1, 1.0 / (double)((size_t)1 << g.lgN), g.lgN, col0, st);
 }
 // row stage.  forward: exchange layout -> X_local [R][N2]; inverse: X_local -> exchange layout (unscaled)
-static int dist_rows(const DistGeom &g, int dir, cplx *xbuf, cplx *X_local, cudaStream_t st) {
+// (rows [rb * R / nrb, (rb + 1) * R / nrb) only: a row is an item, Bc elements apart in the exchange layout)
+static int dist_rows(const DistGeom &g, int dir, cplx *xbuf, cplx *X_local, cudaStream_t st, int rb = 0, int nrb = 1) {
     C2COpts o{};
     o.dir = dir; o.in_order = 1; o.scale = 1.0;
     o.sp_lgbc = ilog2(g.Bc); o.sp_lgnch = ilog2((size_t)g.nch);
     o.sp_chunk_stride = (long long)(g.N1 * g.Bc); o.sp_rank_stride = (long long)(g.R * g.Bc);
-    if (dir > 0) { o.split_in = true; return exec_c2c(xbuf, X_local, g.N2, g.R, g.Bc, g.N2, o, st); }
+    const size_t rows = g.R / (size_t)nrb, r0 = (size_t)rb * rows;
+    xbuf += r0 * g.Bc; X_local += r0 * g.N2;
+    if (dir > 0) { o.split_in = true; return exec_c2c(xbuf, X_local, g.N2, rows, g.Bc, g.N2, o, st); }
     o.split_out = true;
-    return exec_c2c(X_local, xbuf, g.N2, g.R, g.N2, g.Bc, o, st);
+    return exec_c2c(X_local, xbuf, g.N2, rows, g.N2, g.Bc, o, st);
 }
 
 #ifndef NAPA_EMULATE
@@ -1633,29 +1640,31 @@ static int dist_events() {
     }
     return NAPA_OK;
 }
-// all-to-all of chunk c on the communication stream: slab h of `from` goes to rank h, slab g of `to` comes from rank g
-static int dist_exchange_chunk(const DistGeom &g, int c, const cplx *from, cplx *to) {
-    const size_t slab = g.R * g.Bc, off = (size_t)c * g.N1 * g.Bc;
+// all-to-all of chunk c on the communication stream: slab h of `from` goes to rank h, slab g of `to` comes from rank g;
+// optionally only the rows [rb * R / nrb, (rb + 1) * R / nrb) of every slab (a contiguous piece of it)
+static int dist_exchange_chunk(const DistGeom &g, int c, const cplx *from, cplx *to, int rb = 0, int nrb = 1) {
+    const size_t slab = g.R * g.Bc, piece = slab / (size_t)nrb;
+    const size_t off = (size_t)c * g.N1 * g.Bc + (size_t)rb * piece;
     if (g.P == 1) {
-        CU(cudaMemcpyAsync(to + off, from + off, slab * sizeof(cplx), cudaMemcpyDeviceToDevice, D.comm_stream));
+        CU(cudaMemcpyAsync(to + off, from + off, piece * sizeof(cplx), cudaMemcpyDeviceToDevice, D.comm_stream));
         return NAPA_OK;
     }
 #ifdef NAPA_EMULATE
     return fail(NAPA_E_NCCL, "no NCCL in the emulation build");
 #else
     if (D.peer_ok && to == D.recv) {
-        // slab h of my chunk goes straight into rank h's receive buffer, at my rank's place; copy engines, no SM
+        // piece h of my chunk goes straight into rank h's receive buffer, at my rank's place; copy engines, no SM
         for (int i = 0; i < g.P; i++) {
             const int h = (D.rank + i) % g.P;
-            CU(cudaMemcpyAsync(D.peer_recv[h] + off + (size_t)D.rank * slab, from + off + (size_t)h * slab, slab * sizeof(cplx),
+            CU(cudaMemcpyAsync(D.peer_recv[h] + off + (size_t)D.rank * slab, from + off + (size_t)h * slab, piece * sizeof(cplx),
                                cudaMemcpyDeviceToDevice, D.comm_stream));
         }
         return NAPA_OK;
     }
     NCCL(NC.GroupStart());
     for (int h = 0; h < g.P; h++) {
-        NCCL(NC.Send(from + off + (size_t)h * slab, 2 * slab, ncclDouble, h, D.comm, D.comm_stream));
-        NCCL(NC.Recv(to + off + (size_t)h * slab, 2 * slab, ncclDouble, h, D.comm, D.comm_stream));
+        NCCL(NC.Send(from + off + (size_t)h * slab, 2 * piece, ncclDouble, h, D.comm, D.comm_stream));
+        NCCL(NC.Recv(to + off + (size_t)h * slab, 2 * piece, ncclDouble, h, D.comm, D.comm_stream));
     }
     NCCL(NC.GroupEnd());
     return NAPA_OK;
@@ -1665,35 +1674,60 @@ static int dist_exchange_chunk(const DistGeom &g, int c, const cplx *from, cplx 
 static int exec_dist(cplx *src_local, cplx *dst_local, int lgN, int dir, int nch, cudaStream_t st) {
     DistGeom g;
     OK(dist_geom(lgN, std::max(D.nranks, 1), nch, &g));
-    if (g.nch > 16) return fail(NAPA_E_UNSUPPORTED, "at most 16 chunks");
+    if (g.nch > 8) return fail(NAPA_E_UNSUPPORTED, "at most 8 chunks");
     OK(dist_events());
     OK(dist_buffers(g.N1 * g.B));
     // Peer copies write into OTHER ranks' receive buffers: fence A (every rank is done reading its buffer: the
     // communication stream is already behind the previous call's compute) before the first copy, fence B (every rank's
     // copies have landed) before the data is used.  ncclSend / ncclRecv pairs synchronise by themselves.
     const bool fenced = D.peer_ok && g.P > 1;
+    // The chunk next to the row stage (the last one forward, the first one backward) is exchanged in `nrb` blocks of rows,
+    // so that the row FFTs of a block run while the later blocks are still on the wire: the exchange then overlaps the
+    // column FFTs at one end and the row FFTs at the other.
+    int nrb = G.dist_row_blocks > 0 ? G.dist_row_blocks : 4;
+    while (nrb > 1 && (g.R % (size_t)nrb || g.R / (size_t)nrb < 8 || g.nch + nrb > 15)) nrb >>= 1;
+    // `tail` chunks are exchanged row block by row block ACROSS those chunks, so that block rb is complete -- and its row
+    // FFTs start -- after 1/nrb of that traffic.  Measured (2^30, 8 GPUs, 4 chunks x 4 row blocks): tail 1 4.54 ms,
+    // tail 2 4.64 ms, tail 4 6.11 ms (holding chunks back until the last column pass idles the links): default 1.
+    const int tail = nrb > 1 ? std::max(1, std::min(g.nch, G.dist_tail_chunks > 0 ? G.dist_tail_chunks : 1)) : 1;
     if (dir > 0) {
         if (fenced) OK(dist_fence());
         for (int c = 0; c < g.nch; c++) {
             OK(dist_cols(g, D.rank, c, +1, src_local, D.send, st));
             CU(cudaEventRecord(D.ev_ready[c], st));
-            CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[c], 0));
-            OK(dist_exchange_chunk(g, c, D.send, D.recv));
+            if (c < g.nch - tail) {
+                CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[c], 0));
+                OK(dist_exchange_chunk(g, c, D.send, D.recv));
+            }
         }
-        if (fenced) OK(dist_fence());
-        CU(cudaEventRecord(D.ev_done[0], D.comm_stream));
-        CU(cudaStreamWaitEvent(st, D.ev_done[0], 0));
-        OK(dist_rows(g, +1, D.recv, dst_local, st));
-    } else {
-        OK(dist_rows(g, -1, D.send, src_local, st));
-        CU(cudaEventRecord(D.ev_ready[0], st));
-        CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[0], 0));
-        if (fenced) OK(dist_fence());
-        for (int c = 0; c < g.nch; c++) {
-            OK(dist_exchange_chunk(g, c, D.send, D.recv));
+        CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[g.nch - 1], 0));
+        for (int rb = 0; rb < nrb; rb++) {
+            for (int c = g.nch - tail; c < g.nch; c++) OK(dist_exchange_chunk(g, c, D.send, D.recv, rb, nrb));
             if (fenced) OK(dist_fence());
-            CU(cudaEventRecord(D.ev_done[c], D.comm_stream));
-            CU(cudaStreamWaitEvent(st, D.ev_done[c], 0));
+            CU(cudaEventRecord(D.ev_done[rb], D.comm_stream));
+        }
+        for (int rb = 0; rb < nrb; rb++) {
+            CU(cudaStreamWaitEvent(st, D.ev_done[rb], 0));
+            OK(dist_rows(g, +1, D.recv, dst_local, st, rb, nrb));
+        }
+    } else {
+        if (fenced) OK(dist_fence());
+        for (int rb = 0; rb < nrb; rb++) {
+            OK(dist_rows(g, -1, D.send, src_local, st, rb, nrb));
+            CU(cudaEventRecord(D.ev_ready[rb], st));
+            CU(cudaStreamWaitEvent(D.comm_stream, D.ev_ready[rb], 0));
+            for (int c = 0; c < tail; c++) OK(dist_exchange_chunk(g, c, D.send, D.recv, rb, nrb));
+        }
+        for (int c = 0; c < g.nch; c++) {
+            if (c >= tail) OK(dist_exchange_chunk(g, c, D.send, D.recv));
+            if (c >= tail - 1) {
+                // (the first `tail` chunks complete together, with the last row block)
+                if (fenced) OK(dist_fence());
+                CU(cudaEventRecord(D.ev_done[c], D.comm_stream));
+            }
+        }
+        for (int c = 0; c < g.nch; c++) {
+            CU(cudaStreamWaitEvent(st, D.ev_done[c < tail ? tail - 1 : c], 0));
             OK(dist_cols(g, D.rank, c, -1, dst_local, D.recv, st));
         }
     }
