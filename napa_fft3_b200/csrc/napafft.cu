@@ -478,8 +478,8 @@ static int launch_fused(int la, int lb, int pk, bool win, size_t n, size_t batch
 // planner
 // ------------------------------------------------------------------------------------------
 static std::vector<int> digits_of(int lg, bool natural = false) {
-    if (lg <= 13) return { lg };
-    if (const char *env = getenv("NAPAFFT_DIGITS")) {       // tuning override: "8,12" or "7,7,8" (column digits first)
+    if (lg <= 13 && !(lg >= 8 && getenv("NAPAFFT_DIGITS"))) return { lg };
+    if (const char *env = getenv("NAPAFFT_DIGITS")) {       // tuning / test override: "8,12" or "7,7,8" (column digits first)
         std::vector<int> v; int sum = 0; bool ok = true;
         for (const char *c = env; *c;) { int x = atoi(c); v.push_back(x); sum += x; while (*c && *c != ',') c++; if (*c) c++; }
         for (size_t i = 0; i < v.size(); i++) {
@@ -490,6 +490,7 @@ static std::vector<int> digits_of(int lg, bool natural = false) {
         }
         if (ok && sum == lg && v.size() >= 2 && v.size() <= 3) return v;
     }
+    if (lg <= 13) return { lg };
     // Measured on B200 with tools/sweep_digits.py (profiles/r01_sweep_digits.txt, r01_sweep_digits2.txt).  Column digits first.
     // Two passes while both sides keep >= 64..128-byte contiguous segments; the natural-order row pass
     // stores C*16-byte transposed segments (C = rows per tile), so it leaves the two-digit plans
@@ -1244,10 +1245,12 @@ NAPA_API int napafft_init(int device) {
     return NAPA_OK;
 }
 
+static void dist_release();
 NAPA_API int napafft_shutdown(void) {
     std::lock_guard<std::mutex> lk(G.mu);
     if (!G.inited) return NAPA_OK;
     cudaDeviceSynchronize();
+    dist_release();
     for (int l = 0; l < 14; l++) if (G.stage_tw[l]) { cudaFree(G.stage_tw[l]); G.stage_tw[l] = nullptr; }
     for (auto &kv : G.big) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     G.big.clear();

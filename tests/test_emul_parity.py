@@ -201,3 +201,21 @@ def test_distributed_pipeline_single_rank(napa, lgN):
         assert S.nre(Xl.numpy(), ref[f.freq_index()]) <= S.tol(N)
         assert S.nre(f.inverse(Xl).numpy(), f.scatter_time(x)) <= S.tol(N)
     assert f.nch > 1
+
+
+def test_distributed_pipeline_two_pass_rows(napa, monkeypatch):
+    """rows of the distributed transform long enough for a two-digit plan (2^14 and up on the GPU) read / write the
+    exchange layout in their column-like first pass and their transposed last store; forced here at 2^11 rows with the
+    digit override"""
+    import torch
+    from napa_fft3_b200.dist import DistributedFFT
+    monkeypatch.setenv("NAPAFFT_DIGITS", "7,4")
+    lgN = 22
+    x = S.rand_c(1006, 1 << lgN)
+    ref = np.fft.fft(x)
+    f = DistributedFFT(lgN, napa.b, None, torch.device("cpu"))
+    before = napa.b.launch_count()
+    Xl = f.forward(torch.from_numpy(f.scatter_time(x)))
+    assert napa.b.launch_count() - before >= f.nch + 2 * 4          # column chunks + two passes per row block
+    assert S.nre(Xl.numpy(), ref[f.freq_index()]) <= S.tol(1 << lgN)
+    assert S.nre(f.inverse(Xl).numpy(), f.scatter_time(x)) <= S.tol(1 << lgN)
