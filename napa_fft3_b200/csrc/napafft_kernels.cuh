@@ -508,7 +508,9 @@ struct Stages {
 #pragma unroll
                 for (int s = 0; s < R; s++) sm[smem_phys<LOG2L, PLANAR>(base + s * NS, q)] = v[u + s * NB];
             }
+#ifndef NAPA_MUTANT_NO_EXCHANGE_BARRIER   /* tests/test_emul_orders.py builds a mutant without it to prove that its checks bite */
             Sync::sync();
+#endif
             Next::run(v, sm, tw, t0, q0, t1, q1, hook, PREFETCH ? wn : nullptr);
         }
     }

@@ -12,13 +12,14 @@ DEPS = SRCS + [os.path.join(ROOT, "napa_fft3_b200", "csrc", "napafft_kernels.cuh
                os.path.join(ROOT, "include", "napafft.h"), os.path.join(HERE, "cuda_emul.h")]
 
 
-def build(force=False):
-    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
-        return SO
+def build(force=False, defines=(), so=SO):
+    """defines / so: a differently configured build next to the default one (the mutant of tests/test_emul_orders.py)"""
+    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in DEPS):
+        return so
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DNAPA_EMULATE", "-fvisibility=hidden",
-           "-I", HERE, "-x", "c++", SRCS[0], SRCS[1], "-o", SO, "-lm", "-lpthread"]
+           *["-D" + d for d in defines], "-I", HERE, "-x", "c++", SRCS[0], SRCS[1], "-o", so, "-lm", "-lpthread"]
     subprocess.check_call(cmd)
-    return SO
+    return so
 
 
 if __name__ == "__main__":

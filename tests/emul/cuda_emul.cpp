@@ -2,6 +2,8 @@
 #include "cuda_emul.h"
 
 #include <stdio.h>
+#include <algorithm>
+#include <vector>
 
 namespace napa_emul {
 
@@ -30,6 +32,27 @@ namespace {
 unsigned bar_arrived[16];
 unsigned long long bar_gen[16];
 unsigned long long progress = 0;
+
+// Order in which the live fibers get their turn in one scheduling round.  Fibers only switch at barriers and waits, so a
+// MISSING barrier between a write and another thread's read shows up as a wrong result for the orders in which the
+// reader runs first: the parity tests are therefore also run with NAPA_EMUL_ORDER=reverse and =shuffle (a poor man's
+// racecheck for barrier placement; compute-sanitizer is not available on the GPU pool).
+enum Order { ORDER_FORWARD, ORDER_REVERSE, ORDER_SHUFFLE };
+Order sched_order() {
+    const char *e = getenv("NAPA_EMUL_ORDER");
+    if (!e) return ORDER_FORWARD;
+    return e[0] == 'r' ? ORDER_REVERSE : (e[0] == 's' ? ORDER_SHUFFLE : ORDER_FORWARD);
+}
+unsigned long long rng_state = 0x9e3779b97f4a7c15ull;
+void fill_order(std::vector<size_t> &idx, size_t n, Order o) {
+    idx.resize(n);
+    for (size_t i = 0; i < n; i++) idx[i] = o == ORDER_REVERSE ? n - 1 - i : i;
+    if (o == ORDER_SHUFFLE)
+        for (size_t i = n; i > 1; i--) {
+            rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(idx[i - 1], idx[(size_t)((rng_state >> 33) % i)]);
+        }
+}
 }
 
 static void yield_fiber() {
@@ -86,10 +109,14 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
             f.st = READY;
         }
         for (int i = 0; i < 16; i++) { bar_arrived[i] = 0; }
+        const Order order = sched_order();
+        std::vector<size_t> turn;
         for (;;) {
             unsigned live = 0;
             const unsigned long long before = progress;
-            for (unsigned t = 0; t < nthreads; t++) {
+            fill_order(turn, nthreads, order);
+            for (unsigned k = 0; k < nthreads; k++) {
+                const unsigned t = (unsigned)turn[k];
                 Fiber &f = fibers[t];
                 if (f.st == DONE) continue;
                 current = (int)t;
@@ -179,10 +206,14 @@ void launch_cooperative(dim3 grid, dim3 block, size_t smem, const std::function<
         makecontext(&f.ctx, coop_trampoline, 0);
         f.st = READY;
     }
+    const Order order = sched_order();
+    std::vector<size_t> turn;
     for (;;) {
         size_t live = 0;
         const unsigned long long before = progress;
-        for (size_t i = 0; i < total; i++) {
+        fill_order(turn, total, order);
+        for (size_t k = 0; k < total; k++) {
+            const size_t i = turn[k];
             Fiber &f = coop_fibers[i];
             if (f.st == DONE) continue;
             const unsigned b = (unsigned)(i / nthreads), t = (unsigned)(i % nthreads);
