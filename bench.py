@@ -40,6 +40,14 @@ WORKLOADS = {
 }
 
 
+def bench_config(wl):
+    """the `config` object of the JSON line: identical for the GPU arm and the reference arm"""
+    n, batch, desc = WORKLOADS[wl]
+    l2 = ("inputs_exceed_l2 (no flush: every array of a step is far larger than the 126 MB L2)" if wl != "c1" else
+          "none (one 16 KiB transform per step: latency-bound by definition, its data never leaves L2)")
+    return {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch, "l2_policy": l2}
+
+
 def flops_per_step(wl):
     n, batch, _ = WORKLOADS[wl]
     lg = np.log2(n)
@@ -133,7 +141,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "fp64_complex_fft_gflops", "value": gflops, "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch},
+        "config": bench_config(wl),
         "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -331,7 +339,7 @@ def main():
             "metric": "fp64_complex_fft_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch},
+            "config": bench_config(wl),
             "timing": {"l2_policy": "inputs_exceed_l2 (%.1f GiB per array per GPU)" % (16.0 * n * batch / 2**30),
                        "sharding": "batch-sharded, no collective" if world > 1 else "single GPU",
                        "clock": "CUDA events on the launching stream, max over ranks"},
@@ -551,7 +559,7 @@ def run_c5(args, torch, dist, napa, b, world, rank, local, dev):
             "metric": "fp64_complex_fft_gflops", "value": rec["value"], "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c5", "description": WORKLOADS["c5"][2], "n": rec["n"], "batch_per_gpu": 1},
+            "config": dict(bench_config("c5"), n=rec["n"]),
             "timing": {"l2_policy": "inputs_exceed_l2 (%.1f GiB per GPU)" % (16.0 * rec["n"] / world / 2**30),
                        "layout": "time side: column block of [N1][N2]; freq side: row block k1 of X[k1 + N1*k2]"},
             "clocks": rec["clocks"], "e2e": None, "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"],
