@@ -48,6 +48,14 @@ def bench_config(wl):
     return {"workload": wl, "description": desc, "n": n, "batch_per_gpu": batch, "l2_policy": l2}
 
 
+# FP64 thread-instructions one step EXECUTES (DADD + DMUL + DFMA, dynamic counts of the round-2 `ncu --set full`
+# captures, profiles/r02_ncu_full_*: smsp__inst_executed x the FP64 share of the source-page mix x 32), and the measured
+# FP64 issue rate of the chip (profiles/r02_fp64_rate.txt: 63.4 per clock per SM, 18.44e12 per second): the second
+# roofline of this double-precision path.  For C3 the FP64-pipe time at peak is 92 % of the HBM time at peak.
+FP64_INSTR_PER_STEP = {"c2": 4096 * 65536 * 126.0, "c3": 1024 * 1048576 * 166.0, "c4": 2 * 128e6 * 32.0}
+FP64_PEAK_INSTR_PER_S = 18.44e12
+
+
 def flops_per_step(wl):
     n, batch, _ = WORKLOADS[wl]
     lg = np.log2(n)
@@ -288,6 +296,13 @@ def main():
                 "algorithmic_bytes_per_launch": algorithmic_bytes_per_step(wl) / max(launches_per_step, 1),
                 "avg_launch_ms": ms_per_step / max(launches_per_step, 1),
                 "frac_of_nominal_8000": achieved / 8000.0}
+    if wl in FP64_INSTR_PER_STEP:
+        t_fp64 = FP64_INSTR_PER_STEP[wl] / FP64_PEAK_INSTR_PER_S * 1e3
+        t_hbm = algorithmic_bytes_per_step(wl) / (peak * 1e9) * 1e3
+        roofline["fp64_pipe"] = {"instr_per_step": FP64_INSTR_PER_STEP[wl], "peak_instr_per_s": FP64_PEAK_INSTR_PER_S,
+                                 "ms_at_peak": t_fp64, "hbm_ms_at_peak": t_hbm, "frac": t_fp64 / ms_per_step,
+                                 "note": "second roofline of the path: FP64-pipe time at the measured issue rate "
+                                         "(profiles/r02_fp64_rate.txt) next to the HBM time at the measured copy bandwidth"}
 
     # ---- e2e: the same step through the host-buffer C ABI (pinned host arrays, PCIe inside) ----
     e2e = None
