@@ -238,20 +238,16 @@ static int ensure_scratch(cudaStream_t st, size_t bytes, cplx **out) {
 // tile kinds (lane maps): 0 column-like, 1 row-like, 2 row-like load + transposed store
 enum { KIND_COL = 0, KIND_ROW = 1, KIND_ROWT = 2 };
 typedef void (*pass_fn)(const PassParams);
-template <int K, int V> static pass_fn pass_kernel_k(int l) {
-    switch (l) {
-    case 4: return napa::fft_pass_kernel<4, K, V>;
-    case 5: return napa::fft_pass_kernel<5, K, V>;
-    case 6: return napa::fft_pass_kernel<6, K, V>;
-    case 7: return napa::fft_pass_kernel<7, K, V>;
-    case 8: return napa::fft_pass_kernel<8, K, V>;
-    case 9: return napa::fft_pass_kernel<9, K, V>;
-    case 10: return napa::fft_pass_kernel<10, K, V>;
-    case 11: return napa::fft_pass_kernel<11, K, V>;
-    case 12: return napa::fft_pass_kernel<12, K, V>;
-    case 13: return napa::fft_pass_kernel<13, K, V>;
-    }
-    return nullptr;
+// The kernel templates are instantiated in napafft_tables.cu, which the build compiles once per table slice
+// (NAPA_TABLE = pass0 / pass1 / pass2 / fused / fused_tma) in parallel: one translation unit took five minutes.
+namespace napa {
+pass_fn pass_kernel_table_v0(int l, int kind);
+pass_fn pass_kernel_table_v1(int l, int kind);
+pass_fn pass_kernel_table_v2(int l, int kind);
+typedef void (*fused_fn)(const FusedParams);
+typedef void (*fused_tma_fn)(const FusedTmaParams);
+fused_fn fused_kernel_table(int la, int lb, int pk, bool win);
+fused_tma_fn fused_tma_kernel_table(int la, int lb, int pk, bool win);
 }
 // variant: 0 every fusion path, 1 lean, 2 lean + window (napafft_kernels.cuh: variant_flags)
 static int pass_variant(unsigned flags) {
@@ -261,9 +257,7 @@ static int pass_variant(unsigned flags) {
 }
 static pass_fn pass_kernel(int l, int kind, int variant) {
     if (l < 7 && kind != KIND_ROW) kind = KIND_COL;   // small L: one lane map (see kind_lm); KIND_ROW = dense-rows variant
-    if (variant == 1) return kind == KIND_COL ? pass_kernel_k<0, 1>(l) : (kind == KIND_ROW ? pass_kernel_k<1, 1>(l) : pass_kernel_k<2, 1>(l));
-    if (variant == 2) return kind == KIND_COL ? pass_kernel_k<0, 2>(l) : (kind == KIND_ROW ? pass_kernel_k<1, 2>(l) : pass_kernel_k<2, 2>(l));
-    return kind == KIND_COL ? pass_kernel_k<0, 0>(l) : (kind == KIND_ROW ? pass_kernel_k<1, 0>(l) : pass_kernel_k<2, 0>(l));
+    return variant == 1 ? napa::pass_kernel_table_v1(l, kind) : (variant == 2 ? napa::pass_kernel_table_v2(l, kind) : napa::pass_kernel_table_v0(l, kind));
 }
 
 static int set_kernel_attrs() {
@@ -299,28 +293,11 @@ static int launch_pass(int l, int kind, PassParams &p, long long ntiles, cudaStr
 }
 
 // fused two-pass kernels: (first-executed digit, second digit, plan kind, window fusions compiled in)
-typedef void (*fused_fn)(const napa::FusedParams);
-#define NAPA_FUSED_CASE(a, b)                                                                     \
-    if (la == a && lb == b) {                                                                     \
-        if (win) return pk == 0 ? napa::fft_fused_kernel<a, b, 0, true> : (pk == 1 ? napa::fft_fused_kernel<a, b, 1, true> : napa::fft_fused_kernel<a, b, 2, true>); \
-        return pk == 0 ? napa::fft_fused_kernel<a, b, 0, false> : (pk == 1 ? napa::fft_fused_kernel<a, b, 1, false> : napa::fft_fused_kernel<a, b, 2, false>); \
-    }
-static fused_fn fused_kernel(int la, int lb, int pk, bool win) {
-    NAPA_FUSED_CASE(7, 7) NAPA_FUSED_CASE(7, 8) NAPA_FUSED_CASE(8, 7) NAPA_FUSED_CASE(8, 8)
-    NAPA_FUSED_CASE(9, 9) NAPA_FUSED_CASE(9, 10) NAPA_FUSED_CASE(10, 9) NAPA_FUSED_CASE(10, 10)
-    return nullptr;
-}
-typedef void (*fused_tma_fn)(const napa::FusedTmaParams);
-#define NAPA_FUSED_TMA_CASE(a, b)                                                                 \
-    if (la == a && lb == b) {                                                                     \
-        if (win) return pk == 0 ? napa::fft_fused_tma_kernel<a, b, 0, true> : (pk == 1 ? napa::fft_fused_tma_kernel<a, b, 1, true> : napa::fft_fused_tma_kernel<a, b, 2, true>); \
-        return pk == 0 ? napa::fft_fused_tma_kernel<a, b, 0, false> : (pk == 1 ? napa::fft_fused_tma_kernel<a, b, 1, false> : napa::fft_fused_tma_kernel<a, b, 2, false>); \
-    }
+using napa::fused_fn;
+using napa::fused_tma_fn;
+static fused_fn fused_kernel(int la, int lb, int pk, bool win) { return napa::fused_kernel_table(la, lb, pk, win); }
 // TMA-fed variant: 2048-point tiles only (a column tile is one tensor-map box of <= 256 rows)
-static fused_tma_fn fused_tma_kernel(int la, int lb, int pk, bool win) {
-    NAPA_FUSED_TMA_CASE(7, 7) NAPA_FUSED_TMA_CASE(7, 8) NAPA_FUSED_TMA_CASE(8, 7) NAPA_FUSED_TMA_CASE(8, 8)
-    return nullptr;
-}
+static fused_tma_fn fused_tma_kernel(int la, int lb, int pk, bool win) { return napa::fused_tma_kernel_table(la, lb, pk, win); }
 #ifndef NAPA_EMULATE
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,

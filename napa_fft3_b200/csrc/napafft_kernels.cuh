@@ -1339,6 +1339,7 @@ fft_fused_tma_kernel(const NAPA_GRID_CONSTANT FusedTmaParams P) {
     }
 }
 
+#ifndef NAPA_TABLES_ONLY   /* the small, non-template kernels below belong to napafft.cu alone */
 // ------------------------------------------------------------------------------------------
 // n <= 8: one thread per transform
 // ------------------------------------------------------------------------------------------
@@ -1606,5 +1607,7 @@ __global__ void __launch_bounds__(256) cmul_pointwise_kernel(cplx *a, const cplx
     const long long item = gid / n, i = gid - item * n;
     a[gid] = cmul(a[gid], b[item * b_stride + i]);
 }
+
+#endif  // NAPA_TABLES_ONLY
 
 }  // namespace napa
